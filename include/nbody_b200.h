@@ -1,0 +1,188 @@
+/*
+ * nbody_b200.h — C ABI of libnbody_b200.so: the all-pairs softened-gravity leapfrog hot path of
+ * nuclearbombmods/nbody-cosmological-simulation, as hand-written sm_100a CUDA.
+ *
+ * The reference has no FFI layer: its boundary is the Python surface of simulation.py /
+ * quantization.py / metrics.py.  Each entry point below replaces the ATen op
+ * stream of one reference function; the citation names the reference lines it stands in for.
+ * The Python shell (nbody_cosmological_simulation_b200/) binds these with ctypes; INTEGRATION.md
+ * shows the stub a reference maintainer would add.
+ *
+ * Conventions (binding for every function):
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers owned by the caller;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it;
+ *   - no allocation, no host synchronisation, no global mutable state inside the library;
+ *     scratch memory is passed in (`workspace`), sized by the nb_*_bytes() helpers (host-only);
+ *   - return value: 0 = NB_OK, otherwise an NbStatus code; nb_error_string() explains it;
+ *   - dtype codes: NB_F32 / NB_F64 — the dtype of the simulation state (positions/velocities);
+ *   - `dim` is the spatial dimension D, 2 or 3; (n, D) arrays are row-major contiguous.
+ */
+#ifndef NBODY_B200_H_
+#define NBODY_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define NB_ABI_VERSION 1
+
+typedef enum NbStatus {
+    NB_OK = 0,
+    NB_ERR_INVALID_ARGUMENT = 1,   /* bad dim / dtype / mode / size / null pointer / misalignment */
+    NB_ERR_UNSUPPORTED = 2,        /* combination not implemented (said loudly, never a fallback) */
+    NB_ERR_WORKSPACE_TOO_SMALL = 3,
+    NB_ERR_NO_DEVICE = 4,          /* no sm_100 device / kernel image cannot run here */
+    NB_ERR_CUDA_BASE = 1000        /* NB_ERR_CUDA_BASE + cudaError_t */
+} NbStatus;
+
+typedef enum NbDType { NB_F32 = 0, NB_F64 = 1 } NbDType;
+
+/* quantization.py:10-18 PrecisionMode, same order */
+typedef enum NbMode {
+    NB_MODE_FLOAT64 = 0,
+    NB_MODE_FLOAT32 = 1,
+    NB_MODE_BFLOAT16 = 2,
+    NB_MODE_FLOAT16 = 3,
+    NB_MODE_INT8_SIM = 4,
+    NB_MODE_INT4_SIM = 5,
+    NB_MODE_CUSTOM = 6
+} NbMode;
+
+/* Slots of the device-side scalar block (int64[NB_SCALAR_SLOTS]).  Values are order-preserving
+ * 64-bit keys of doubles (nb_key_from_double) so that cross-rank MIN/MAX all-reduces on the raw
+ * int64 tensor are meaningful. */
+enum {
+    NB_SLOT_MAX_D2 = 0,     /* max over all pairs of d² (state dtype, widened)      quantization.py:113 */
+    NB_SLOT_ACC_MIN = 1,    /* min over all n·D accelerations                      quantization.py:78  */
+    NB_SLOT_ACC_MAX = 2,    /* max over all n·D accelerations                      quantization.py:79  */
+    NB_SLOT_VAL_MIN = 3,    /* generic tensor min (nb_tensor_minmax)                                   */
+    NB_SLOT_VAL_MAX = 4,    /* generic tensor max                                                     */
+    NB_SLOT_RADIUS_MAX = 5, /* max radius                                           metrics.py:51      */
+    NB_SCALAR_SLOTS = 8
+};
+
+/* ---- library / device ------------------------------------------------------------------- */
+int nb_abi_version(void);
+const char* nb_error_string(int status);
+/* Fills SM count and compute capability of the current device; NB_ERR_NO_DEVICE if none. */
+int nb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+int64_t nb_key_from_double(double v);
+double nb_double_from_key(int64_t key);
+
+/* ---- packed source set -------------------------------------------------------------------
+ * The force / energy kernels stream sources from a chunk-major packed buffer that TMA bulk copies
+ * (cp.async.bulk) move into shared memory.  One chunk = NB_CHUNK_UNITS units; a unit is two fp32
+ * sources or one fp64 source (16 B of x,y + 16 B (D=3: z,m) or 8 B (D=2: m)).
+ * Padding sources (mass 0, position of the last real source) fill the last chunk. */
+#define NB_CHUNK_UNITS 128
+int64_t nb_chunk_sources(int dtype);                       /* 256 for NB_F32, 128 for NB_F64 */
+int64_t nb_chunk_bytes(int dim, int dtype);                /* 4096 (D=3) / 3072 (D=2)         */
+int64_t nb_num_chunks(int64_t n, int dtype);               /* ceil(n / nb_chunk_sources)      */
+int64_t nb_packed_bytes(int64_t n, int dim, int dtype);    /* nb_num_chunks * nb_chunk_bytes  */
+
+/* Replaces the `pos.unsqueeze(0)` / `masses.unsqueeze(0)` operands of simulation.py:83,105,181-186.
+ * pos: (n, dim) of `dtype`; mass: (n,) of `mass_dtype`; packed: nb_packed_bytes(n, dim, dtype). */
+int nb_pack_sources(const void* pos, const void* mass, int64_t n, int dim, int dtype, int mass_dtype,
+                    void* packed, void* stream);
+
+/* ---- force evaluation: GalaxySimulation._compute_accelerations, simulation.py:74-118 ------- */
+/* Bytes of scratch nb_accel needs for n_targets targets (partial sums of the j-split). */
+int64_t nb_accel_workspace_bytes(int64_t n_targets, int dim);
+
+/* INT8_SIM / INT4_SIM / CUSTOM pass 1 (quantization.py:112-113): max over all target×source
+ * pairs of d² (exact reference rounding sequence, state dtype) -> scalars[NB_SLOT_MAX_D2] (atomic
+ * max; reset it with nb_reset_scalars first).  After a cross-rank MAX all-reduce of that slot the
+ * LUT is built by nb_build_level_table. */
+int nb_max_dist_sq(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt,
+                   int dim, int dtype, double eps_sq, int64_t* scalars, void* stream);
+
+/* Bytes of the level table for `levels` grid levels. */
+int64_t nb_level_table_bytes(int levels);
+/* quantization.py:106-127 collapsed to a table: for each level k the snapped value u_k, the force
+ * factor rn(rn(1/u_k^1.5)*G) (simulation.py:97-101) and the exact d² threshold at which
+ * round((log(t)-lo)/(hi-lo)*(L-1)) steps from k-1 to k (bisection over the float bit pattern with
+ * the reference's own op order).  lo = log(max(eps², min_dist_sq)) because the diagonal is part of
+ * the tensor; hi comes from scalars[NB_SLOT_MAX_D2]. */
+int nb_build_level_table(const int64_t* scalars, int dtype, double eps_sq, double min_dist_sq, double G,
+                         int levels, void* table, void* stream);
+
+/* acc_out[i,:] = Σ_j f(q(d²_ij))·m_j·(x_j − x_i)  for targets pos_tgt[0:n_tgt] against all n_src
+ * packed sources (self pairs contribute exactly 0, as `* (1 - eye)` at simulation.py:108).
+ * mode selects q (quantization.py:21-71); int modes read `level_table`.
+ * Output dtype: NB_F64 when dtype==NB_F64 or mode==NB_MODE_FLOAT64 (torch promotion at
+ * quantization.py:45), else NB_F32.  For INT8/INT4 this is the PRE-snap acceleration; the min/max
+ * over all outputs is folded into scalars[NB_SLOT_ACC_MIN/MAX] (quantization.py:78-79) and the snap
+ * itself is nb_snap_accelerations or fused into nb_kdk. */
+int nb_accel(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt, int dim,
+             int dtype, int mode, double G, double eps_sq, const void* level_table, int levels,
+             void* acc_out, int64_t* scalars, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* quantize_force -> _grid_quantize(a, levels) (simulation.py:115-116, quantization.py:74-88) with the
+ * global min/max taken from scalars[NB_SLOT_ACC_MIN/MAX]; in place on acc (n*dim values, acc_dtype). */
+int nb_snap_accelerations(void* acc, int64_t count, int acc_dtype, int levels, const int64_t* scalars,
+                          void* stream);
+
+/* ---- integrator: GalaxySimulation.step, simulation.py:120-143 ------------------------------ */
+typedef enum NbKdkPhase {
+    NB_KDK_KICK_DRIFT = 0,       /* v=v+a*(dt/2); x=x+v*dt                      simulation.py:132,135   */
+    NB_KDK_KICK = 1,             /* v=v+a*(dt/2)                                simulation.py:141       */
+    NB_KDK_KICK_KICK_DRIFT = 2   /* :141 of tick t fused with :132,135 of tick t+1 (same roundings)    */
+} NbKdkPhase;
+/* One HBM round trip of the state per tick.  mul and add are separately rounded (no FMA) and dt/2,
+ * dt are cast to the state dtype first, exactly as torch does.  If snap_levels > 0 the acceleration
+ * is first snapped to the linear grid (nb_snap_accelerations semantics) and written back to `acc`.
+ * x_out/v_out may alias x_in/v_in.  If packed_out != NULL (phases with a drift) the packed source
+ * record of every updated particle is emitted as well (mass: (n,) of mass_dtype). */
+int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_out, int64_t n, int dim,
+           int dtype, double dt, int phase, int snap_levels, const int64_t* scalars,
+           const void* mass, int mass_dtype, void* packed_out, void* stream);
+
+/* ---- energies: simulation.py:170-196 ------------------------------------------------------- */
+int64_t nb_energy_workspace_bytes(int64_t n_targets);
+/* out[0] = Σ_{i in targets} m_i Σ_{j≠i} m_j / sqrt(d²_ij)   (double; caller applies −G/2 and sums ranks).
+ * The targets must be members of the source set (an i-range shard of it): the j == i term is removed
+ * by subtracting the identical expression once per target. */
+int nb_potential_energy(const void* packed_src, int64_t n_src, const void* pos_tgt, const void* mass_tgt,
+                        int64_t n_tgt, int dim, int dtype, int mass_dtype, double eps_sq,
+                        double* out, void* workspace, int64_t workspace_bytes, void* stream);
+/* out[0] = Σ_i m_i Σ_k v_ik²  (double; caller applies 0.5). */
+int nb_kinetic_energy(const void* vel, const void* mass, int64_t n, int dim, int dtype, int mass_dtype,
+                      double* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- rotation curve: metrics.py:25-78 ------------------------------------------------------ */
+/* scalars[NB_SLOT_RADIUS_MAX] = max_i sqrt(Σ_k x_ik²) (metrics.py:48,51), atomic max. */
+int nb_radius_max(const void* pos, int64_t n, int dim, int dtype, int64_t* scalars, void* stream);
+/* Half-open bins [edges[b], edges[b+1]) in the state dtype; sum_vt[b] += |x·vy − y·vx| / max(r, 0.1),
+ * count[b] += 1 (metrics.py:55-57,65-69).  sum_vt/count must be zeroed by the caller. */
+int nb_rotation_curve(const void* pos, const void* vel, int64_t n, int dim, int dtype, const void* edges,
+                      int num_bins, double* sum_vt, int64_t* count, void* stream);
+
+/* ---- free-standing quantisers: quantization.py:74-127 -------------------------------------- */
+int nb_reset_scalars(int64_t* scalars, void* stream);
+/* scalars[VAL_MIN/VAL_MAX] = min/max of `in` (after clamp(min=clamp_min) and log() when log_space). */
+int nb_tensor_minmax(const void* in, int64_t count, int dtype, int log_space, double clamp_min,
+                     int64_t* scalars, void* stream);
+/* _grid_quantize (quantization.py:74-88) with min/max from scalars[VAL_MIN/VAL_MAX]. */
+int nb_grid_quantize(const void* in, void* out, int64_t count, int dtype, int levels, const int64_t* scalars,
+                     void* stream);
+/* _grid_quantize_safe (quantization.py:91-127) with log_min/log_max from scalars[VAL_MIN/VAL_MAX];
+ * index_out (int32, may be NULL) receives the level index round(normalized). */
+int nb_grid_quantize_safe(const void* in, void* out, int32_t* index_out, int64_t count, int dtype, int levels,
+                          double min_val, const int64_t* scalars, void* stream);
+/* The snap itself on identical pre-snap values: index_out[i] = round-half-even(normalized[i]). */
+int nb_snap_index(const void* normalized, int32_t* index_out, int64_t count, int dtype, void* stream);
+/* FLOAT16 / BFLOAT16 round trip of quantization.py:53,56 (mode = NB_MODE_FLOAT16 | NB_MODE_BFLOAT16). */
+int nb_round_trip(const void* in, void* out, int64_t count, int dtype, int mode, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBODY_B200_H_ */

@@ -1,0 +1,115 @@
+"""ctypes binding of libnbody_b200.so (C ABI declared in include/nbody_b200.h).
+
+The shared library is the product: every function here forwards raw device pointers, sizes and the
+current CUDA stream to a hand-written sm_100a kernel.  There is no CPU path and no fallback — if the
+library is missing, or a tensor is not on a CUDA device, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTER
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnbody_b200.so")
+
+# dtype / mode / phase codes (include/nbody_b200.h)
+NB_F32, NB_F64 = 0, 1
+MODE_CODES = {"float64": 0, "float32": 1, "bfloat16": 2, "float16": 3, "int8_sim": 4, "int4_sim": 5, "custom": 6}
+KDK_KICK_DRIFT, KDK_KICK, KDK_KICK_KICK_DRIFT = 0, 1, 2
+SLOT_MAX_D2, SLOT_ACC_MIN, SLOT_ACC_MAX, SLOT_VAL_MIN, SLOT_VAL_MAX, SLOT_RADIUS_MAX = 0, 1, 2, 3, 4, 5
+SCALAR_SLOTS = 8
+ABI_VERSION = 1
+
+_P = c_void_p
+# name -> (restype, argtypes); must list every symbol include/nbody_b200.h declares
+PROTOTYPES = {
+    "nb_abi_version": (c_int, []),
+    "nb_error_string": (c_char_p, [c_int]),
+    "nb_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "nb_key_from_double": (c_int64, [c_double]),
+    "nb_double_from_key": (c_double, [c_int64]),
+    "nb_chunk_sources": (c_int64, [c_int]),
+    "nb_chunk_bytes": (c_int64, [c_int, c_int]),
+    "nb_num_chunks": (c_int64, [c_int64, c_int]),
+    "nb_packed_bytes": (c_int64, [c_int64, c_int, c_int]),
+    "nb_pack_sources": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
+    "nb_accel_workspace_bytes": (c_int64, [c_int64, c_int]),
+    "nb_max_dist_sq": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, c_double, _P, _P]),
+    "nb_level_table_bytes": (c_int64, [c_int]),
+    "nb_build_level_table": (c_int, [_P, c_int, c_double, c_double, c_double, c_int, _P, _P]),
+    "nb_accel": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_double, c_double, _P, c_int, _P, _P, _P,
+                         c_int64, _P]),
+    "nb_snap_accelerations": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
+    "nb_kdk": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_double, c_int, c_int, _P, _P, c_int, _P, _P]),
+    "nb_energy_workspace_bytes": (c_int64, [c_int64]),
+    "nb_potential_energy": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_double, _P, _P, c_int64, _P]),
+    "nb_kinetic_energy": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, _P, c_int64, _P]),
+    "nb_radius_max": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
+    "nb_rotation_curve": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, _P, _P, _P]),
+    "nb_reset_scalars": (c_int, [_P, _P]),
+    "nb_tensor_minmax": (c_int, [_P, c_int64, c_int, c_int, c_double, _P, _P]),
+    "nb_grid_quantize": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P]),
+    "nb_grid_quantize_safe": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_double, _P, _P]),
+    "nb_snap_index": (c_int, [_P, _P, c_int64, c_int, _P]),
+    "nb_round_trip": (c_int, [_P, _P, c_int64, c_int, c_int, _P]),
+}
+
+
+class NbodyLibraryError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libnbody_b200.so once; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NbodyLibraryError(
+            f"{LIB_PATH} is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"(or nbody_cosmological_simulation_b200/csrc/build.sh). There is no CPU/PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)           # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.nb_abi_version() != ABI_VERSION:
+        raise NbodyLibraryError(f"ABI mismatch: library {lib.nb_abi_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = load().nb_error_string(status).decode()
+        raise NbodyLibraryError(f"libnbody_b200 {what} failed with status {status}: {msg}")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return NB_F32
+    if t.dtype == torch.float64:
+        return NB_F64
+    raise NbodyLibraryError(f"unsupported tensor dtype {t.dtype}: the CUDA path takes float32 or float64 state")
+
+
+def require_cuda(*tensors: torch.Tensor):
+    for t in tensors:
+        if not t.is_cuda:
+            raise NbodyLibraryError(
+                "nbody_cosmological_simulation_b200 runs on CUDA devices only (B200, sm_100a); got a tensor on "
+                f"'{t.device}'. There is deliberately no CPU fallback.")
+
+
+def ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)

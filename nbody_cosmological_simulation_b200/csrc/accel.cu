@@ -1,0 +1,468 @@
+// All-pairs softened-gravity force evaluation — GalaxySimulation._compute_accelerations,
+// simulation.py:74-118, with the d² quantisers of quantization.py:21-127 fused in.
+//
+// Roofline: FP32 (FMA pipe) / FP64 (DFMA pipe) issue-bound, 0 algorithmic HBM bytes per pair: the
+// packed source set (16 B per fp32 particle) is L2-resident and streamed through shared memory.
+//   fp32, D=3: per source PAIR and target 12 packed fp32x2 ops (FADD2/FFMA2/FMUL2 = 24 FMA-pipe
+//   cycles per warp) + 2 MUFU.RSQ;  D=2: 9 packed ops + 2 MUFU.RSQ.
+//   fp64, D=3: 16 DFMA-class ops + 1 MUFU.RSQ64H per pair (seed + one cubic-corrected Newton step).
+// Accumulation: per-thread fp32x2 partial sums over one chunk (256 sources), flushed into fp64
+// accumulators per chunk => the Σ_j error does not grow with N (SURVEY.md §7 "hard parts").
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include "stream.cuh"
+
+namespace nb {
+
+enum QMode { Q_F32 = 0, Q_F16 = 1, Q_BF16 = 2, Q_LUT = 3, Q_F64 = 4 };
+
+struct AccelArgs {
+    const char* src;          // packed sources
+    int64_t n_chunks;
+    const void* pos_tgt;      // (n_tgt, DIM) state dtype
+    int64_t n_tgt;
+    int chunks_per_split;
+    double* partial;          // [splits][n_tgt][DIM]
+    double eps_sq;
+    const void* table;        // level table (Q_LUT)
+    int levels;
+};
+
+// Level table layout (Q_LUT): float4 entry[k] = { T_{k+1}, g_k, g_{k+1}, 0 } for k = 0..L-1, preceded by a
+// 16-byte header { lo2 (log2 of lower bound), scale (levels-1)/(hi2-lo2), min_val, degenerate flag }.
+struct LevelHeader { float lo2, scale, min_val, degenerate; };
+
+// ======================================================================================================
+// fp32 state, packed-pair arithmetic
+// ======================================================================================================
+template <int DIM_, int QMODE, int IPT, int THREADS_>
+struct ForceF32 {
+    static constexpr int DIM = DIM_;
+    static constexpr int THREADS = THREADS_;
+    float2 nx[IPT], ny[IPT], nz[IPT];      // {-x_i, -x_i}: targets, negated and duplicated for packed adds
+    float2 ax[IPT], ay[IPT], az[IPT];      // chunk-local sums; .x = even sources, .y = odd sources
+    double sx[IPT], sy[IPT], sz[IPT];      // running fp64 sums
+    float2 eps2;
+    const float4* lut;                     // shared-memory copy of the level table (Q_LUT)
+    float lo2, scale, min_val;
+
+    __device__ __forceinline__ void init(const AccelArgs& a, const float4* lut_smem) {
+        const float* pos = reinterpret_cast<const float*>(a.pos_tgt);
+#pragma unroll
+        for (int t = 0; t < IPT; ++t) {
+            int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            if (i >= a.n_tgt) i = a.n_tgt - 1;
+            const float x = pos[i * DIM + 0], y = pos[i * DIM + 1], z = DIM == 3 ? pos[i * DIM + 2] : 0.f;
+            nx[t] = make_float2(-x, -x); ny[t] = make_float2(-y, -y); nz[t] = make_float2(-z, -z);
+            ax[t] = ay[t] = az[t] = make_float2(0.f, 0.f);
+            sx[t] = sy[t] = sz[t] = 0.0;
+        }
+        const float e = (float)a.eps_sq;                // softening_sq cast to the tensor dtype (simulation.py:86)
+        eps2 = make_float2(e, e);
+        lut = lut_smem;
+        if (QMODE == Q_LUT) {
+            const float4 h = lut_smem[0];
+            lo2 = h.x; scale = h.y; min_val = h.z;
+        }
+    }
+
+    // d² for a source pair: fused (fp32 mode, tolerance 1e-5) or the reference's exact rounding
+    // sequence (modes whose next step is a snap: fp16/bf16 round trip, log-grid index).
+    __device__ __forceinline__ float2 dist_sq(float2 dx, float2 dy, float2 dz) const {
+        if (QMODE == Q_F32) {
+            float2 d2 = fma2(dx, dx, eps2);
+            d2 = fma2(dy, dy, d2);
+            if (DIM == 3) d2 = fma2(dz, dz, d2);
+            return d2;
+        } else {
+            // scalar _rn ops on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (seen in SASS),
+            // which would change d² by an ulp and flip fp16/bf16/grid snaps; scalar FMUL/FADD are left alone.
+            float sx = __fadd_rn(__fmul_rn(dx.x, dx.x), __fmul_rn(dy.x, dy.x));   // rn(rn(dx²)+rn(dy²))   simulation.py:86
+            float sy = __fadd_rn(__fmul_rn(dx.y, dx.y), __fmul_rn(dy.y, dy.y));
+            if (DIM == 3) {
+                sx = __fadd_rn(sx, __fmul_rn(dz.x, dz.x));                           // rn(· + rn(dz²))
+                sy = __fadd_rn(sy, __fmul_rn(dz.y, dz.y));
+            }
+            return make_float2(__fadd_rn(sx, eps2.x), __fadd_rn(sy, eps2.y));        // rn(· + ε²)
+        }
+    }
+
+    __device__ __forceinline__ float lut_factor(float d2) const {
+        // t = clamp(d², min); k = round((log t − lo)/(hi − lo)·(L−1)) found exactly from a MUFU.LG2
+        // estimate biased to k−1 ≤ k_lo ≤ k plus one comparison against the exact threshold T_{k_lo+1}.
+        const float t = fmaxf(d2, min_val);
+        float kf = fmaf(lg2_approx(t) - lo2, scale, -0.5f + 1.0f / 64.0f);   // (n_est − ½ + margin): rint() below gives floor-ish
+        kf = fminf(fmaxf(kf, 0.f), (float)(levels_m1));
+        const int k_lo = __float2int_rn(kf);
+        const float4 e = lut[1 + k_lo];
+        return t >= e.x ? e.z : e.y;
+    }
+    int levels_m1;
+
+    __device__ __forceinline__ void chunk(const unsigned char* s, int64_t) {
+        const float4* A = reinterpret_cast<const float4*>(s);
+        const float4* B4 = reinterpret_cast<const float4*>(s + kChunkABytes);
+        const float2* B2 = reinterpret_cast<const float2*>(s + kChunkABytes);
+#pragma unroll 4
+        for (int p = 0; p < kChunkUnits; ++p) {
+            const float4 a = A[p];
+            const float2 xs = make_float2(a.x, a.y), ys = make_float2(a.z, a.w);
+            float2 zs = make_float2(0.f, 0.f), ms;
+            if (DIM == 3) { const float4 b = B4[p]; zs = make_float2(b.x, b.y); ms = make_float2(b.z, b.w); }
+            else ms = B2[p];
+#pragma unroll
+            for (int t = 0; t < IPT; ++t) {
+                const float2 dx = add2(xs, nx[t]);              // diff = pos[j] − pos[i]   simulation.py:83
+                const float2 dy = add2(ys, ny[t]);
+                float2 dz = make_float2(0.f, 0.f);
+                if (DIM == 3) dz = add2(zs, nz[t]);
+                float2 d2 = dist_sq(dx, dy, dz);
+                float2 w;                                       // m_j · f(d²) without G (hoisted), or with G (LUT)
+                if (QMODE == Q_LUT) {
+                    w = mul2(make_float2(lut_factor(d2.x), lut_factor(d2.y)), ms);
+                } else {
+                    if (QMODE == Q_F16) {                       // dist_sq.half().float()    quantization.py:56
+                        const __half2 h = __floats2half2_rn(d2.x, d2.y);
+                        d2 = __half22float2(h);
+                    } else if (QMODE == Q_BF16) {               // dist_sq.bfloat16().float() quantization.py:53
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(d2.x, d2.y);
+                        d2 = __bfloat1622float2(h);
+                    }
+                    const float2 r = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
+                    w = mul2(mul2(r, r), mul2(r, ms));          // m_j / d²^1.5             simulation.py:97-105
+                }
+                ax[t] = fma2(w, dx, ax[t]);                     // Σ_j w·diff               simulation.py:112
+                ay[t] = fma2(w, dy, ay[t]);
+                if (DIM == 3) az[t] = fma2(w, dz, az[t]);
+            }
+        }
+        // flush the chunk-local fp32 sums into the fp64 accumulators
+#pragma unroll
+        for (int t = 0; t < IPT; ++t) {
+            sx[t] += (double)(ax[t].x + ax[t].y); ax[t] = make_float2(0.f, 0.f);
+            sy[t] += (double)(ay[t].x + ay[t].y); ay[t] = make_float2(0.f, 0.f);
+            if (DIM == 3) { sz[t] += (double)(az[t].x + az[t].y); az[t] = make_float2(0.f, 0.f); }
+        }
+    }
+
+    __device__ __forceinline__ void store(const AccelArgs& a) const {
+        double* out = a.partial + (int64_t)blockIdx.y * a.n_tgt * DIM;
+#pragma unroll
+        for (int t = 0; t < IPT; ++t) {
+            const int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            if (i < a.n_tgt) {
+                out[i * DIM + 0] = sx[t]; out[i * DIM + 1] = sy[t];
+                if (DIM == 3) out[i * DIM + 2] = sz[t];
+            }
+        }
+    }
+};
+
+// ======================================================================================================
+// fp64 state (QMODE Q_F64: all-double; Q_F32/F16/BF16: d² cast down as quantization.py:48-56 does)
+// and "mixed": fp32 state evaluated in FLOAT64 mode (d² formed in fp32 with the reference's exact
+// rounding sequence, then widened — quantization.py:45 applied to an fp32 dist_sq).
+// ======================================================================================================
+__device__ __forceinline__ double mass_over_dist_cubed(double d2, double m) {
+    // m · d2^(-3/2): MUFU.RSQ64H seed y0 (rel. err δ≈2^-22), e = 1 − d2·y0² ≈ 2δ,
+    // d2^(-3/2) = y0³ (1−e)^(-3/2) = y0³ (1 + e(3/2 + 15/8 e) + O(e³))   — 7 DFMA-class ops, error ~1e-19+ulp
+    const double y0 = rsqrt64h(d2);
+    const double t = y0 * y0;
+    const double e = fma(-d2, t, 1.0);
+    const double ce = fma(1.875, e, 1.5) * e;
+    const double w = (m * y0) * t;
+    return fma(w, ce, w);
+}
+
+template <int DIM_, int QMODE, int IPT, int THREADS_>
+struct ForceF64 {
+    static constexpr int DIM = DIM_;
+    static constexpr int THREADS = THREADS_;
+    double xi[IPT], yi[IPT], zi[IPT];
+    double sx[IPT], sy[IPT], sz[IPT];
+    double eps2;
+
+    __device__ __forceinline__ void init(const AccelArgs& a, const float4*) {
+        const double* pos = reinterpret_cast<const double*>(a.pos_tgt);
+#pragma unroll
+        for (int t = 0; t < IPT; ++t) {
+            int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            if (i >= a.n_tgt) i = a.n_tgt - 1;
+            xi[t] = pos[i * DIM + 0]; yi[t] = pos[i * DIM + 1]; zi[t] = DIM == 3 ? pos[i * DIM + 2] : 0.0;
+            sx[t] = sy[t] = sz[t] = 0.0;
+        }
+        eps2 = a.eps_sq;
+    }
+    __device__ __forceinline__ void chunk(const unsigned char* s, int64_t) {
+        const double2* A = reinterpret_cast<const double2*>(s);
+        const double2* B2 = reinterpret_cast<const double2*>(s + kChunkABytes);
+        const double* B1 = reinterpret_cast<const double*>(s + kChunkABytes);
+#pragma unroll 2
+        for (int p = 0; p < kChunkUnits; ++p) {
+            const double2 a = A[p];
+            double zs = 0.0, m;
+            if (DIM == 3) { const double2 b = B2[p]; zs = b.x; m = b.y; } else m = B1[p];
+#pragma unroll
+            for (int t = 0; t < IPT; ++t) {
+                const double dx = a.x - xi[t], dy = a.y - yi[t], dz = DIM == 3 ? zs - zi[t] : 0.0;
+                double d2 = fma(dx, dx, eps2);
+                d2 = fma(dy, dy, d2);
+                if (DIM == 3) d2 = fma(dz, dz, d2);
+                double w;
+                if (QMODE == Q_F64) {
+                    w = mass_over_dist_cubed(d2, m);
+                } else {
+                    float u = (float)d2;                                         // dist_sq.float()
+                    if (QMODE == Q_F16) u = __half2float(__float2half_rn(u));
+                    if (QMODE == Q_BF16) u = __bfloat162float(__float2bfloat16_rn(u));
+                    const float r = rsqrt_approx(u);
+                    w = (double)((r * r) * (r * (float)m));
+                }
+                sx[t] = fma(w, dx, sx[t]);
+                sy[t] = fma(w, dy, sy[t]);
+                if (DIM == 3) sz[t] = fma(w, dz, sz[t]);
+            }
+        }
+    }
+    __device__ __forceinline__ void store(const AccelArgs& a) const {
+        double* out = a.partial + (int64_t)blockIdx.y * a.n_tgt * DIM;
+#pragma unroll
+        for (int t = 0; t < IPT; ++t) {
+            const int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            if (i < a.n_tgt) {
+                out[i * DIM + 0] = sx[t]; out[i * DIM + 1] = sy[t];
+                if (DIM == 3) out[i * DIM + 2] = sz[t];
+            }
+        }
+    }
+};
+
+template <int DIM_, int IPT, int THREADS_>
+struct ForceMixed {       // fp32 sources/targets, FLOAT64 mode
+    static constexpr int DIM = DIM_;
+    static constexpr int THREADS = THREADS_;
+    float xi[IPT], yi[IPT], zi[IPT];
+    double sx[IPT], sy[IPT], sz[IPT];
+    float eps2;
+
+    __device__ __forceinline__ void init(const AccelArgs& a, const float4*) {
+        const float* pos = reinterpret_cast<const float*>(a.pos_tgt);
+#pragma unroll
+        for (int t = 0; t < IPT; ++t) {
+            int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            if (i >= a.n_tgt) i = a.n_tgt - 1;
+            xi[t] = pos[i * DIM + 0]; yi[t] = pos[i * DIM + 1]; zi[t] = DIM == 3 ? pos[i * DIM + 2] : 0.f;
+            sx[t] = sy[t] = sz[t] = 0.0;
+        }
+        eps2 = (float)a.eps_sq;
+    }
+    __device__ __forceinline__ void one(float xs, float ys, float zs, float m, int t) {
+        const float dx = __fsub_rn(xs, xi[t]), dy = __fsub_rn(ys, yi[t]);
+        const float dz = DIM == 3 ? __fsub_rn(zs, zi[t]) : 0.f;
+        float s = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        if (DIM == 3) s = __fadd_rn(s, __fmul_rn(dz, dz));
+        const double d2 = (double)__fadd_rn(s, eps2);                      // fp32 d², widened (quantization.py:45)
+        const double w = mass_over_dist_cubed(d2, (double)m);
+        sx[t] = fma(w, (double)dx, sx[t]);
+        sy[t] = fma(w, (double)dy, sy[t]);
+        if (DIM == 3) sz[t] = fma(w, (double)dz, sz[t]);
+    }
+    __device__ __forceinline__ void chunk(const unsigned char* s, int64_t) {
+        const float4* A = reinterpret_cast<const float4*>(s);
+        const float4* B4 = reinterpret_cast<const float4*>(s + kChunkABytes);
+        const float2* B2 = reinterpret_cast<const float2*>(s + kChunkABytes);
+#pragma unroll 2
+        for (int p = 0; p < kChunkUnits; ++p) {
+            const float4 a = A[p];
+            float z0 = 0.f, z1 = 0.f, m0, m1;
+            if (DIM == 3) { const float4 b = B4[p]; z0 = b.x; z1 = b.y; m0 = b.z; m1 = b.w; }
+            else { const float2 b = B2[p]; m0 = b.x; m1 = b.y; }
+#pragma unroll
+            for (int t = 0; t < IPT; ++t) {
+                one(a.x, a.z, z0, m0, t);
+                one(a.y, a.w, z1, m1, t);
+            }
+        }
+    }
+    __device__ __forceinline__ void store(const AccelArgs& a) const {
+        double* out = a.partial + (int64_t)blockIdx.y * a.n_tgt * DIM;
+#pragma unroll
+        for (int t = 0; t < IPT; ++t) {
+            const int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            if (i < a.n_tgt) {
+                out[i * DIM + 0] = sx[t]; out[i * DIM + 1] = sy[t];
+                if (DIM == 3) out[i * DIM + 2] = sz[t];
+            }
+        }
+    }
+};
+
+// ======================================================================================================
+// kernels
+// ======================================================================================================
+constexpr int kMaxLevelsSmem = 4096;      // level table entries staged in shared memory (64 KB + header)
+
+template <class Consumer, bool USE_LUT>
+__global__ void __launch_bounds__(Consumer::THREADS + 32) accel_kernel(const AccelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const bool is_consumer = threadIdx.x < Consumer::THREADS;
+    const float4* lut_smem = nullptr;
+    if (USE_LUT) {
+        // the level table sits behind the streaming stages
+        float4* dst = reinterpret_cast<float4*>(smem + stream_smem_bytes(Consumer::DIM));
+        const float4* srcT = reinterpret_cast<const float4*>(a.table);
+        for (int k = threadIdx.x; k < a.levels + 1; k += blockDim.x) dst[k] = srcT[k];
+        lut_smem = dst;
+        __syncthreads();
+    }
+    Consumer cons;
+    if (is_consumer) cons.init(a, lut_smem);
+    if constexpr (USE_LUT) cons.levels_m1 = a.levels - 1;
+    const int64_t c0 = (int64_t)blockIdx.y * a.chunks_per_split;
+    const int64_t c1 = min(a.n_chunks, c0 + (int64_t)a.chunks_per_split);
+    stream_sources(a.src, c0, c1, cons);
+    if (is_consumer) cons.store(a);
+}
+
+// acc_out[i,k] = scale · Σ_splits partial;  optional min/max of the outputs -> scalars (quantization.py:78-79)
+template <typename TOUT, bool MINMAX>
+__global__ void __launch_bounds__(256) accel_finalize_kernel(const double* __restrict__ partial, int splits, int64_t count,
+                                                             double scale, TOUT* __restrict__ out, int64_t* __restrict__ scalars) {
+    __shared__ long long red[32];
+    long long kmin = kKeyHighest, kmax = kKeyLowest;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int sp = 0; sp < splits; ++sp) s += partial[(int64_t)sp * count + e];
+        const TOUT v = (TOUT)(s * scale);
+        out[e] = v;
+        if (MINMAX) {
+            const long long k = key_from_double((double)v);
+            kmin = k < kmin ? k : kmin;
+            kmax = k > kmax ? k : kmax;
+        }
+    }
+    if (MINMAX) {
+        kmin = block_reduce(kmin, OpMin(), (long long)kKeyHighest, red);
+        kmax = block_reduce(kmax, OpMax(), (long long)kKeyLowest, red);
+        if (threadIdx.x == 0) {
+            atomicMin(reinterpret_cast<long long*>(scalars + NB_SLOT_ACC_MIN), kmin);
+            atomicMax(reinterpret_cast<long long*>(scalars + NB_SLOT_ACC_MAX), kmax);
+        }
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+struct SplitPlan { int blocks_i; int splits; int chunks_per_split; };
+
+inline SplitPlan plan_splits(int64_t n_tgt, int64_t n_chunks, int targets_per_block, int max_splits_by_ws) {
+    SplitPlan p;
+    p.blocks_i = (int)((n_tgt + targets_per_block - 1) / targets_per_block);
+    // enough CTAs for ~12 per SM so that the tail (partial last wave) stays below a few percent
+    const int64_t want = (int64_t)kNumSMsB200 * 12;
+    int64_t s = (want + p.blocks_i - 1) / p.blocks_i;
+    if (s > n_chunks) s = n_chunks;
+    if (s > max_splits_by_ws) s = max_splits_by_ws;
+    if (s > 65535) s = 65535;
+    if (s < 1) s = 1;
+    p.chunks_per_split = (int)((n_chunks + s - 1) / s);
+    p.splits = (int)((n_chunks + p.chunks_per_split - 1) / p.chunks_per_split);
+    return p;
+}
+
+constexpr int kForceThreads = 256;
+constexpr int kForceIPT = 2;
+constexpr int kTargetsPerBlock = kForceThreads * kForceIPT;
+constexpr int kMaxSplits = 64;
+
+template <class Consumer, bool USE_LUT>
+int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, int* splits_out) {
+    AccelArgs a = a0;
+    const int64_t per_split = a.n_tgt * Consumer::DIM * (int64_t)sizeof(double);
+    int64_t max_by_ws = workspace_bytes / per_split;
+    if (max_by_ws < 1) return NB_ERR_WORKSPACE_TOO_SMALL;
+    if (max_by_ws > kMaxSplits) max_by_ws = kMaxSplits;
+    const SplitPlan p = plan_splits(a.n_tgt, a.n_chunks, Consumer::THREADS * kForceIPT, (int)max_by_ws);
+    a.chunks_per_split = p.chunks_per_split;
+    int smem = stream_smem_bytes(Consumer::DIM);
+    if (USE_LUT) smem += (a.levels + 1) * 16;
+    auto kern = accel_kernel<Consumer, USE_LUT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    kern<<<dim3(p.blocks_i, p.splits), Consumer::THREADS + 32, smem, st>>>(a);
+    NB_CUDA_LAUNCH_CHECK();
+    *splits_out = p.splits;
+    return NB_OK;
+}
+
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" int64_t nb_accel_workspace_bytes(int64_t n_targets, int dim) {
+    if (n_targets <= 0 || (dim != 2 && dim != 3)) return 0;
+    // room for the largest j-split the planner may choose for this many targets
+    const int blocks_i = (int)((n_targets + kTargetsPerBlock - 1) / kTargetsPerBlock);
+    int64_t s = ((int64_t)kNumSMsB200 * 12 + blocks_i - 1) / blocks_i;
+    if (s > kMaxSplits) s = kMaxSplits;
+    if (s < 1) s = 1;
+    return s * n_targets * dim * (int64_t)sizeof(double);
+}
+
+extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt, int dim, int dtype,
+                        int mode, double G, double eps_sq, const void* level_table, int levels, void* acc_out,
+                        int64_t* scalars, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!packed_src || !pos_tgt || !acc_out || !workspace || n_src <= 0 || n_tgt <= 0 || (dim != 2 && dim != 3))
+        return NB_ERR_INVALID_ARGUMENT;
+    if (dtype != NB_F32 && dtype != NB_F64) return NB_ERR_INVALID_ARGUMENT;
+    if (mode < NB_MODE_FLOAT64 || mode > NB_MODE_CUSTOM) return NB_ERR_INVALID_ARGUMENT;
+    const bool lut = mode == NB_MODE_INT8_SIM || mode == NB_MODE_INT4_SIM || mode == NB_MODE_CUSTOM;
+    if (lut && (!level_table || levels < 2 || !scalars)) return NB_ERR_INVALID_ARGUMENT;
+    if (lut && levels > kMaxLevelsSmem) return NB_ERR_UNSUPPORTED;
+    if (lut && dtype == NB_F64) return NB_ERR_UNSUPPORTED;       // fp64 state + int modes: no caller in the reference
+    cudaStream_t st = (cudaStream_t)stream;
+
+    AccelArgs a{};
+    a.src = (const char*)packed_src;
+    a.n_chunks = nb_num_chunks(n_src, dtype);
+    a.pos_tgt = pos_tgt;
+    a.n_tgt = n_tgt;
+    a.partial = (double*)workspace;
+    a.eps_sq = eps_sq;
+    a.table = level_table;
+    a.levels = levels;
+
+    int splits = 0, rc = NB_ERR_INVALID_ARGUMENT;
+    constexpr int TH = kForceThreads, IPT = kForceIPT;
+#define NB_F32_CASE(D, Q, LUT) rc = launch_accel<ForceF32<D, Q, IPT, TH>, LUT>(a, workspace_bytes, st, &splits)
+#define NB_F64_CASE(D, Q) rc = launch_accel<ForceF64<D, Q, IPT, TH>, false>(a, workspace_bytes, st, &splits)
+    if (dtype == NB_F32) {
+        if (mode == NB_MODE_FLOAT64) {
+            if (dim == 2) rc = launch_accel<ForceMixed<2, IPT, TH>, false>(a, workspace_bytes, st, &splits);
+            else rc = launch_accel<ForceMixed<3, IPT, TH>, false>(a, workspace_bytes, st, &splits);
+        } else if (mode == NB_MODE_FLOAT32) { if (dim == 2) NB_F32_CASE(2, Q_F32, false); else NB_F32_CASE(3, Q_F32, false); }
+        else if (mode == NB_MODE_FLOAT16) { if (dim == 2) NB_F32_CASE(2, Q_F16, false); else NB_F32_CASE(3, Q_F16, false); }
+        else if (mode == NB_MODE_BFLOAT16) { if (dim == 2) NB_F32_CASE(2, Q_BF16, false); else NB_F32_CASE(3, Q_BF16, false); }
+        else { if (dim == 2) NB_F32_CASE(2, Q_LUT, true); else NB_F32_CASE(3, Q_LUT, true); }
+    } else {
+        if (mode == NB_MODE_FLOAT64) { if (dim == 2) NB_F64_CASE(2, Q_F64); else NB_F64_CASE(3, Q_F64); }
+        else if (mode == NB_MODE_FLOAT32) { if (dim == 2) NB_F64_CASE(2, Q_F32); else NB_F64_CASE(3, Q_F32); }
+        else if (mode == NB_MODE_FLOAT16) { if (dim == 2) NB_F64_CASE(2, Q_F16); else NB_F64_CASE(3, Q_F16); }
+        else if (mode == NB_MODE_BFLOAT16) { if (dim == 2) NB_F64_CASE(2, Q_BF16); else NB_F64_CASE(3, Q_BF16); }
+    }
+#undef NB_F32_CASE
+#undef NB_F64_CASE
+    if (rc != NB_OK) return rc;
+
+    // finalize: Σ splits, ×G (float modes: G was hoisted out of the pair loop; LUT factors already carry G)
+    const bool out_f64 = dtype == NB_F64 || mode == NB_MODE_FLOAT64;
+    const bool minmax = mode == NB_MODE_INT8_SIM || mode == NB_MODE_INT4_SIM;
+    const double scale = lut ? 1.0 : G;
+    const int64_t count = n_tgt * dim;
+    int64_t blocks = (count + 255) / 256;
+    if (blocks > kNumSMsB200 * 8) blocks = kNumSMsB200 * 8;
+    if (out_f64) accel_finalize_kernel<double, false><<<(int)blocks, 256, 0, st>>>(a.partial, splits, count, scale, (double*)acc_out, scalars);
+    else if (minmax) accel_finalize_kernel<float, true><<<(int)blocks, 256, 0, st>>>(a.partial, splits, count, scale, (float*)acc_out, scalars);
+    else accel_finalize_kernel<float, false><<<(int)blocks, 256, 0, st>>>(a.partial, splits, count, scale, (float*)acc_out, scalars);
+    NB_CUDA_LAUNCH_CHECK();
+    return NB_OK;
+}

@@ -1,0 +1,243 @@
+// Packed-source emission and the fused kick-drift-kick (+ acceleration grid snap) integrator.
+// Reference semantics: simulation.py:120-143 (step), quantization.py:74-88 (_grid_quantize).
+// HBM-bound elementwise work: one thread per "unit" (two fp32 particles / one fp64 particle), every
+// array read once and written once per tick, contiguous per warp.
+#include "common.cuh"
+
+namespace nb {
+
+// ---- exact (non-contracted) arithmetic in the state dtype ------------------------------------------
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float rint_even(float a) { return rintf(a); }
+__device__ __forceinline__ double rint_even(double a) { return rint(a); }
+
+// _grid_quantize on one value given the global min/max (quantization.py:84-86); each op rounded alone.
+template <typename T>
+struct LinearGrid {
+    T lo, span, lm1;
+    bool active;     // false when (max - min) < 1e-10  (quantization.py:81) -> values pass through
+    __device__ LinearGrid(const int64_t* scalars, int slot_min, int slot_max, int levels) {
+        lo = (T)double_from_key(scalars[slot_min]);
+        T hi = (T)double_from_key(scalars[slot_max]);
+        span = sub_rn(hi, lo);
+        lm1 = (T)(levels - 1);
+        active = !(span < (T)1e-10);
+    }
+    __device__ __forceinline__ T snap(T a) const {
+        if (!active) return a;
+        T k = rint_even(mul_rn(div_rn(sub_rn(a, lo), span), lm1));
+        return add_rn(mul_rn(div_rn(k, lm1), span), lo);
+    }
+};
+
+// ---- packed source record writers ------------------------------------------------------------------
+// fp32: unit = particles (2u, 2u+1); A = {x0,x1,y0,y1}; B = {z0,z1,m0,m1} (D=3) | {m0,m1} (D=2)
+template <int DIM>
+__device__ __forceinline__ void emit_unit_f32(char* packed, int64_t unit, const float* p0, const float* p1, float m0, float m1) {
+    const int64_t chunk = unit / kChunkUnits;
+    const int u = (int)(unit % kChunkUnits);
+    char* base = packed + chunk * (int64_t)chunk_bytes(DIM);
+    *reinterpret_cast<float4*>(base + u * 16) = make_float4(p0[0], p1[0], p0[1], p1[1]);
+    if (DIM == 3) *reinterpret_cast<float4*>(base + kChunkABytes + u * 16) = make_float4(p0[2], p1[2], m0, m1);
+    else          *reinterpret_cast<float2*>(base + kChunkABytes + u * 8) = make_float2(m0, m1);
+}
+// fp64: unit = particle u; A = {x,y}; B = {z,m} (D=3) | {m} (D=2)
+template <int DIM>
+__device__ __forceinline__ void emit_unit_f64(char* packed, int64_t unit, const double* p, double m) {
+    const int64_t chunk = unit / kChunkUnits;
+    const int u = (int)(unit % kChunkUnits);
+    char* base = packed + chunk * (int64_t)chunk_bytes(DIM);
+    *reinterpret_cast<double2*>(base + u * 16) = make_double2(p[0], p[1]);
+    if (DIM == 3) *reinterpret_cast<double2*>(base + kChunkABytes + u * 16) = make_double2(p[2], m);
+    else          *reinterpret_cast<double*>(base + kChunkABytes + u * 8) = m;
+}
+
+template <typename TM>
+__device__ __forceinline__ double load_mass(const void* mass, int64_t i) { return (double)reinterpret_cast<const TM*>(mass)[i]; }
+
+// ---- nb_pack_sources -------------------------------------------------------------------------------
+template <typename T, int DIM, typename TM>
+__global__ void __launch_bounds__(256) pack_kernel(const T* __restrict__ pos, const TM* __restrict__ mass, int64_t n,
+                                                   char* __restrict__ packed, int64_t n_units) {
+    constexpr int UP = sizeof(T) == 4 ? 2 : 1;      // particles per unit
+    for (int64_t unit = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; unit < n_units;
+         unit += (int64_t)gridDim.x * blockDim.x) {
+        T p[UP][3];
+        T m[UP];
+#pragma unroll
+        for (int h = 0; h < UP; ++h) {
+            int64_t i = unit * UP + h;
+            bool real = i < n;
+            int64_t src = real ? i : n - 1;          // padding: position of the last real source, mass 0
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) p[h][k] = pos[src * DIM + k];
+            m[h] = real ? (T)mass[src] : (T)0;
+        }
+        if constexpr (sizeof(T) == 4) emit_unit_f32<DIM>(packed, unit, p[0], p[UP - 1], m[0], m[UP - 1]);
+        else emit_unit_f64<DIM>(packed, unit, p[0], m[0]);
+    }
+}
+
+// ---- nb_kdk ----------------------------------------------------------------------------------------
+template <typename T, int DIM, typename TM, int PHASE>
+__global__ void __launch_bounds__(256) kdk_kernel(const T* __restrict__ x_in, const T* __restrict__ v_in, T* __restrict__ acc,
+                                                  T* __restrict__ x_out, T* __restrict__ v_out, int64_t n, T half_dt, T dt,
+                                                  int snap_levels, const int64_t* __restrict__ scalars,
+                                                  const TM* __restrict__ mass, char* __restrict__ packed, int64_t n_units) {
+    constexpr int UP = sizeof(T) == 4 ? 2 : 1;
+    LinearGrid<T> grid(scalars, NB_SLOT_ACC_MIN, NB_SLOT_ACC_MAX, snap_levels > 0 ? snap_levels : 2);
+    const bool snap = snap_levels > 0;
+    for (int64_t unit = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; unit < n_units;
+         unit += (int64_t)gridDim.x * blockDim.x) {
+        T px[UP][3];
+        T pm[UP];
+#pragma unroll
+        for (int h = 0; h < UP; ++h) {
+            const int64_t i = unit * UP + h;
+            const bool real = i < n;
+            if (real) {
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) {
+                    const int64_t e = i * DIM + k;
+                    T a = acc[e];
+                    if (snap) { a = grid.snap(a); acc[e] = a; }
+                    T v = v_in[e];
+                    const T kick = mul_rn(a, half_dt);
+                    v = add_rn(v, kick);                                     // simulation.py:141 / :132
+                    if (PHASE == NB_KDK_KICK_KICK_DRIFT) v = add_rn(v, kick); // :132 of the next tick
+                    v_out[e] = v;
+                    if (PHASE != NB_KDK_KICK) {
+                        T x = add_rn(x_in[e], mul_rn(v, dt));                // :135
+                        x_out[e] = x;
+                        px[h][k] = x;
+                    }
+                }
+                if (PHASE != NB_KDK_KICK && packed) pm[h] = (T)mass[i];
+            }
+        }
+        if (PHASE != NB_KDK_KICK && packed) {
+            // padding half of the last unit / padding units of the last chunk
+#pragma unroll
+            for (int h = 0; h < UP; ++h) {
+                const int64_t i = unit * UP + h;
+                if (i >= n) {
+                    // position of the last real particle after its own update: recompute it here (cheap, rare)
+                    const int64_t s = n - 1;
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) {
+                        const int64_t e = s * DIM + k;
+                        T a = acc[e];
+                        if (snap) a = grid.snap(a);
+                        T v = v_in[e];
+                        const T kick = mul_rn(a, half_dt);
+                        v = add_rn(v, kick);
+                        if (PHASE == NB_KDK_KICK_KICK_DRIFT) v = add_rn(v, kick);
+                        px[h][k] = add_rn(x_in[e], mul_rn(v, dt));
+                    }
+                    pm[h] = (T)0;
+                }
+            }
+            if constexpr (sizeof(T) == 4) emit_unit_f32<DIM>(packed, unit, px[0], px[UP - 1], pm[0], pm[UP - 1]);
+            else emit_unit_f64<DIM>(packed, unit, px[0], pm[0]);
+        }
+    }
+}
+
+// ---- nb_snap_accelerations -------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) snap_kernel(T* __restrict__ acc, int64_t count, int levels,
+                                                   const int64_t* __restrict__ scalars) {
+    LinearGrid<T> grid(scalars, NB_SLOT_ACC_MIN, NB_SLOT_ACC_MAX, levels);
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x)
+        acc[e] = grid.snap(acc[e]);
+}
+
+inline int grid_for(int64_t work_items, int threads) {
+    int64_t blocks = (work_items + threads - 1) / threads;
+    const int64_t cap = (int64_t)kNumSMsB200 * 16;          // grid-stride beyond 16 CTAs per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <typename T, int DIM, typename TM>
+int launch_pack(const void* pos, const void* mass, int64_t n, void* packed, cudaStream_t st) {
+    const int64_t n_units = nb_num_chunks(n, sizeof(T) == 4 ? NB_F32 : NB_F64) * kChunkUnits;
+    pack_kernel<T, DIM, TM><<<grid_for(n_units, 256), 256, 0, st>>>((const T*)pos, (const TM*)mass, n, (char*)packed, n_units);
+    NB_CUDA_LAUNCH_CHECK();
+    return NB_OK;
+}
+
+template <typename T, int DIM, typename TM, int PHASE>
+int launch_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_out, int64_t n, double dt,
+               int snap_levels, const int64_t* scalars, const void* mass, void* packed, cudaStream_t st) {
+    constexpr int UP = sizeof(T) == 4 ? 2 : 1;
+    // with packed output the padding units of the last chunk are written too
+    const int64_t n_units = packed ? nb_num_chunks(n, sizeof(T) == 4 ? NB_F32 : NB_F64) * kChunkUnits : (n + UP - 1) / UP;
+    kdk_kernel<T, DIM, TM, PHASE><<<grid_for(n_units, 256), 256, 0, st>>>(
+        (const T*)x_in, (const T*)v_in, (T*)acc, (T*)x_out, (T*)v_out, n, (T)(dt / 2), (T)dt, snap_levels, scalars,
+        (const TM*)mass, (char*)packed, n_units);
+    NB_CUDA_LAUNCH_CHECK();
+    return NB_OK;
+}
+
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" int nb_pack_sources(const void* pos, const void* mass, int64_t n, int dim, int dtype, int mass_dtype,
+                               void* packed, void* stream) {
+    if (!pos || !mass || !packed || n <= 0 || (dim != 2 && dim != 3)) return NB_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = (cudaStream_t)stream;
+#define NB_PACK_CASE(T, DT, TM, MDT, D) \
+    if (dtype == DT && mass_dtype == MDT && dim == D) return launch_pack<T, D, TM>(pos, mass, n, packed, st);
+    NB_PACK_CASE(float, NB_F32, float, NB_F32, 2) NB_PACK_CASE(float, NB_F32, float, NB_F32, 3)
+    NB_PACK_CASE(float, NB_F32, double, NB_F64, 2) NB_PACK_CASE(float, NB_F32, double, NB_F64, 3)
+    NB_PACK_CASE(double, NB_F64, float, NB_F32, 2) NB_PACK_CASE(double, NB_F64, float, NB_F32, 3)
+    NB_PACK_CASE(double, NB_F64, double, NB_F64, 2) NB_PACK_CASE(double, NB_F64, double, NB_F64, 3)
+#undef NB_PACK_CASE
+    return NB_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_out, int64_t n, int dim, int dtype,
+                      double dt, int phase, int snap_levels, const int64_t* scalars, const void* mass, int mass_dtype,
+                      void* packed_out, void* stream) {
+    if (!v_in || !acc || !v_out || n <= 0 || (dim != 2 && dim != 3)) return NB_ERR_INVALID_ARGUMENT;
+    if (phase != NB_KDK_KICK && (!x_in || !x_out)) return NB_ERR_INVALID_ARGUMENT;
+    if (snap_levels < 0 || snap_levels == 1 || (snap_levels > 0 && !scalars)) return NB_ERR_INVALID_ARGUMENT;
+    if (packed_out && (!mass || phase == NB_KDK_KICK)) return NB_ERR_INVALID_ARGUMENT;
+    if (!scalars) return NB_ERR_INVALID_ARGUMENT;       // the snap grid constructor always reads the block
+    // padding records re-derive the last particle's new position from x_in: never run in place then
+    if (packed_out && (x_out == x_in || v_out == v_in)) return NB_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!mass) mass_dtype = dtype;
+#define NB_KDK_CASE(T, DT, TM, MDT, D, PH)                                  \
+    if (dtype == DT && mass_dtype == MDT && dim == D && phase == PH)        \
+        return launch_kdk<T, D, TM, PH>(x_in, v_in, acc, x_out, v_out, n, dt, snap_levels, scalars, mass, packed_out, st);
+#define NB_KDK_PHASES(T, DT, TM, MDT, D) \
+    NB_KDK_CASE(T, DT, TM, MDT, D, NB_KDK_KICK_DRIFT) NB_KDK_CASE(T, DT, TM, MDT, D, NB_KDK_KICK) NB_KDK_CASE(T, DT, TM, MDT, D, NB_KDK_KICK_KICK_DRIFT)
+    NB_KDK_PHASES(float, NB_F32, float, NB_F32, 2) NB_KDK_PHASES(float, NB_F32, float, NB_F32, 3)
+    NB_KDK_PHASES(float, NB_F32, double, NB_F64, 2) NB_KDK_PHASES(float, NB_F32, double, NB_F64, 3)
+    NB_KDK_PHASES(double, NB_F64, float, NB_F32, 2) NB_KDK_PHASES(double, NB_F64, float, NB_F32, 3)
+    NB_KDK_PHASES(double, NB_F64, double, NB_F64, 2) NB_KDK_PHASES(double, NB_F64, double, NB_F64, 3)
+#undef NB_KDK_PHASES
+#undef NB_KDK_CASE
+    return NB_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int nb_snap_accelerations(void* acc, int64_t count, int acc_dtype, int levels, const int64_t* scalars, void* stream) {
+    if (!acc || !scalars || count <= 0 || levels < 2) return NB_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (acc_dtype == NB_F32) snap_kernel<float><<<grid_for(count, 256), 256, 0, st>>>((float*)acc, count, levels, scalars);
+    else if (acc_dtype == NB_F64) snap_kernel<double><<<grid_for(count, 256), 256, 0, st>>>((double*)acc, count, levels, scalars);
+    else return NB_ERR_INVALID_ARGUMENT;
+    NB_CUDA_LAUNCH_CHECK();
+    return NB_OK;
+}

@@ -1,0 +1,72 @@
+// Source-streaming skeleton shared by every O(N²) kernel (force, max-d², potential energy).
+//
+// A CTA owns a block of target particles (registers) and a contiguous range of packed source chunks.
+// One extra producer warp feeds a ring of shared-memory stages with TMA bulk copies (cp.async.bulk +
+// mbarrier complete_tx); the consumer warps walk each stage chunk by chunk with warp-broadcast
+// LDS.128 reads and release it through an "empty" mbarrier.  Warps may drift apart by up to
+// kStages-1 stages, so there is no CTA-wide barrier in the steady state.
+#pragma once
+#include "common.cuh"
+
+namespace nb {
+
+constexpr int kStages = 3;
+constexpr int kStageChunks = 4;                 // 16 KB (D=3) / 12 KB (D=2) per stage
+constexpr int kBarrierBytes = 128;              // full[kStages] + empty[kStages] mbarriers, padded
+
+__host__ __device__ inline int stream_smem_bytes(int dim) { return kBarrierBytes + kStages * kStageChunks * chunk_bytes(dim); }
+
+// Consumer concept:
+//   static constexpr int DIM, THREADS (consumer threads; the CTA has THREADS + 32);
+//   __device__ void chunk(const unsigned char* smem_chunk, int64_t chunk_index);   // all consumer threads
+template <class Consumer>
+__device__ __forceinline__ void stream_sources(const char* __restrict__ src, int64_t c0, int64_t c1, Consumer& cons) {
+    constexpr int DIM = Consumer::DIM;
+    constexpr int NCW = Consumer::THREADS / 32;     // consumer warps
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t bar0 = smem_u32(smem);
+    unsigned char* data = smem + kBarrierBytes;
+    const int cb = chunk_bytes(DIM);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_chunks = (int)(c1 - c0);
+    const int n_iters = (n_chunks + kStageChunks - 1) / kStageChunks;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar0 + 8 * s, 1);                  // full: one arrive (+tx bytes) by the producer
+            mbar_init(bar0 + 8 * (kStages + s), NCW);    // empty: one arrive per consumer warp
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        // ---------------- producer warp: one elected lane issues the bulk copies ----------------
+        if (lane == 0) {
+            for (int it = 0; it < n_iters; ++it) {
+                const int s = it % kStages;
+                if (it >= kStages) mbar_wait(bar0 + 8 * (kStages + s), ((it / kStages) - 1) & 1);
+                const int first = it * kStageChunks;
+                const int cnt = min(kStageChunks, n_chunks - first);
+                const uint32_t bytes = (uint32_t)(cnt * cb);
+                mbar_arrive_expect_tx(bar0 + 8 * s, bytes);
+                tma_bulk_g2s(smem_u32(data + s * kStageChunks * cb), src + (c0 + first) * (int64_t)cb, bytes, bar0 + 8 * s);
+            }
+        }
+    } else {
+        // ---------------- consumer warps ----------------
+        for (int it = 0; it < n_iters; ++it) {
+            const int s = it % kStages;
+            mbar_wait(bar0 + 8 * s, (it / kStages) & 1);
+            const int first = it * kStageChunks;
+            const int cnt = min(kStageChunks, n_chunks - first);
+            const unsigned char* stage = data + s * kStageChunks * cb;
+            for (int c = 0; c < cnt; ++c) cons.chunk(stage + c * cb, c0 + first + c);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * (kStages + s));
+        }
+    }
+}
+
+}  // namespace nb

@@ -1,0 +1,331 @@
+"""All-pairs leapfrog N-body engine — the API of the reference's simulation.py on sm_100a kernels.
+
+`GalaxySimulation` keeps the constructor, attributes, methods and the overridable
+`_compute_accelerations()` hook of `/root/reference/simulation.py:12-196`; `run_comparison` mirrors
+:199-250.  What changes is the body: instead of ~23-55 ATen launches over N×N temporaries per tick
+ a tick is
+
+    nb_kdk(KICK_DRIFT | KICK_KICK_DRIFT)   one pass over x,v,a; also emits the packed source records
+    [int modes: nb_max_dist_sq -> nb_build_level_table]
+    nb_accel                               tiled O(N²) pair loop, sources streamed by TMA bulk copies
+    nb_kdk(KICK)                           only when the state must be observable (end of step()/callback)
+
+with every scalar that the reference pulls to the host (`if max - min < 1e-10`) kept on the device.
+The arithmetic contract (which ops are separately rounded, dtype promotion, reduction tolerances) is
+SURVEY.md Appendix A.  There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .quantization import PrecisionMode, levels_for_mode
+
+_INT_FORCE_SNAP = {PrecisionMode.INT8_SIM: 256, PrecisionMode.INT4_SIM: 16}      # simulation.py:115
+
+
+class _DeviceBuffers:
+    """Per-simulation scratch owned by torch (the library itself never allocates)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.scalars = torch.empty(L.SCALAR_SLOTS, dtype=torch.int64, device=device)
+        self._bytes = {}
+
+    def bytes(self, key: str, nbytes: int) -> torch.Tensor:
+        buf = self._bytes.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.device)
+            self._bytes[key] = buf
+        return buf
+
+
+class GalaxySimulation:
+    """N-body gravitational simulation with configurable precision (reference simulation.py:12-196)."""
+
+    def __init__(
+        self,
+        positions: torch.Tensor,
+        velocities: torch.Tensor,
+        masses: torch.Tensor,
+        precision_mode: PrecisionMode = PrecisionMode.FLOAT64,
+        G: float = 0.001,
+        softening: float = 0.1,
+        dt: float = 0.01,
+        device: torch.device = None,
+    ):
+        self.device = torch.device(device) if device is not None else positions.device
+        self.precision_mode = precision_mode
+        self.G = G
+        self.softening = softening
+        self.softening_sq = softening ** 2
+        self.dt = dt
+
+        self.positions = positions.clone().to(self.device)
+        self.velocities = velocities.clone().to(self.device)
+        self.masses = masses.clone().to(self.device)
+        self.num_stars = len(masses)
+
+        self._buffers: Optional[_DeviceBuffers] = None
+        self._packed_key = None
+
+        # reference simulation.py:69 — one force evaluation at construction
+        self.accelerations = self._compute_accelerations()
+        self.tick = 0
+
+    # ------------------------------------------------------------------------------------------
+    # plumbing
+    # ------------------------------------------------------------------------------------------
+    def _buf(self) -> _DeviceBuffers:
+        buf = getattr(self, "_buffers", None)           # subclasses may run code before super().__init__
+        if buf is None or buf.device != self.positions.device:
+            buf = _DeviceBuffers(self.positions.device)
+            self._buffers = buf
+        return buf
+
+    @staticmethod
+    def _is_stock(obj, name: str) -> bool:
+        return getattr(type(obj), name) is getattr(GalaxySimulation, name)
+
+    def _state(self):
+        """(x, v, m) as contiguous CUDA fp32/fp64 tensors; x and v share one dtype."""
+        x, v, m = self.positions, self.velocities, self.masses
+        L.require_cuda(x, v, m)
+        if x.dim() != 2 or x.shape[1] not in (2, 3):
+            raise L.NbodyLibraryError(f"positions must be (N, 2) or (N, 3); got {tuple(x.shape)}")
+        return x.contiguous(), v.contiguous(), m.contiguous()
+
+    def _pack(self, x: torch.Tensor, m: torch.Tensor) -> torch.Tensor:
+        """Packed source records for (x, m); cached while the same tensor objects stay unmodified."""
+        buf = self._buf()
+        n, dim = x.shape
+        code = L.dtype_code(x)
+        nbytes = L.load().nb_packed_bytes(n, dim, code)
+        packed = buf.bytes(f"packed{code}", nbytes)
+        key = self._packed_cache_key(x, m, packed)
+        if getattr(self, "_packed_key", None) != key:
+            with torch.cuda.device(x.device):
+                L.check(L.load().nb_pack_sources(L.ptr(x), L.ptr(m), n, dim, code, L.dtype_code(m), L.ptr(packed),
+                                                 L.stream_ptr(x.device)), "nb_pack_sources")
+            self._packed_key = key
+        return packed
+
+    @staticmethod
+    def _packed_cache_key(x, m, packed):
+        return (x.data_ptr(), x._version, m.data_ptr(), m._version, x.dtype, tuple(x.shape), packed.data_ptr())
+
+    # ------------------------------------------------------------------------------------------
+    # force evaluation — reference simulation.py:74-118
+    # ------------------------------------------------------------------------------------------
+    def _accelerations_raw(self, x: torch.Tensor, m: torch.Tensor, packed: torch.Tensor):
+        """Pre-snap accelerations of all stars and the force-snap level count (0 = none)."""
+        lib, buf = L.load(), self._buf()
+        n, dim = x.shape
+        code = L.dtype_code(x)
+        mode = self.precision_mode
+        mode_code = L.MODE_CODES[mode.value]
+        levels = levels_for_mode(mode) or 0
+        out_dtype = torch.float64 if (code == L.NB_F64 or mode == PrecisionMode.FLOAT64) else torch.float32
+        acc = torch.empty((n, dim), dtype=out_dtype, device=x.device)
+        ws_bytes = lib.nb_accel_workspace_bytes(n, dim)
+        ws = buf.bytes("accel_ws", ws_bytes)
+        eps_sq = float(self.softening_sq)
+        table = None
+        with torch.cuda.device(x.device):
+            st = L.stream_ptr(x.device)
+            if levels:
+                L.check(lib.nb_reset_scalars(L.ptr(buf.scalars), st), "nb_reset_scalars")
+                L.check(lib.nb_max_dist_sq(L.ptr(packed), n, L.ptr(x), n, dim, code, eps_sq, L.ptr(buf.scalars), st),
+                        "nb_max_dist_sq")
+                table = buf.bytes("level_table", lib.nb_level_table_bytes(levels))
+                L.check(lib.nb_build_level_table(L.ptr(buf.scalars), code, eps_sq, 0.01, float(self.G), levels,
+                                                 L.ptr(table), st), "nb_build_level_table")
+            L.check(lib.nb_accel(L.ptr(packed), n, L.ptr(x), n, dim, code, mode_code, float(self.G), eps_sq,
+                                 L.ptr(table), levels, L.ptr(acc), L.ptr(buf.scalars), L.ptr(ws), ws.numel(), st),
+                    "nb_accel")
+        return acc, _INT_FORCE_SNAP.get(mode, 0)
+
+    def _compute_accelerations(self) -> torch.Tensor:
+        """Gravitational accelerations of all stars in the current precision mode (overridable hook)."""
+        x, _, m = self._state()
+        packed = self._pack(x, m)
+        acc, snap_levels = self._accelerations_raw(x, m, packed)
+        if snap_levels:
+            with torch.cuda.device(x.device):
+                L.check(L.load().nb_snap_accelerations(L.ptr(acc), acc.numel(), L.dtype_code(acc), snap_levels,
+                                                       L.ptr(self._buf().scalars), L.stream_ptr(x.device)),
+                        "nb_snap_accelerations")
+        return acc
+
+    # ------------------------------------------------------------------------------------------
+    # integrator — reference simulation.py:120-158
+    # ------------------------------------------------------------------------------------------
+    def _promoted_state(self, acc: torch.Tensor):
+        """x, v, a in the dtype torch's promotion gives `v + a * scalar` (Appendix A: fp32 ⊕ fp64 → fp64)."""
+        x, v, m = self._state()
+        dt = torch.promote_types(torch.promote_types(x.dtype, v.dtype), acc.dtype)
+        if dt not in (torch.float32, torch.float64):
+            raise L.NbodyLibraryError(f"unsupported state dtype {dt}")
+        return x.to(dt), v.to(dt), m, acc.contiguous().to(dt)
+
+    def _kdk(self, phase: int, x, v, a, m, snap_levels: int = 0, emit_packed: bool = False):
+        lib, buf = L.load(), self._buf()
+        n, dim = v.shape
+        code = L.dtype_code(v)
+        drift = phase != L.KDK_KICK
+        x_out = torch.empty_like(x) if drift else None
+        v_out = torch.empty_like(v)
+        packed = None
+        if emit_packed:
+            packed = buf.bytes(f"packed{code}", lib.nb_packed_bytes(n, dim, code))
+        with torch.cuda.device(v.device):
+            L.check(lib.nb_kdk(L.ptr(x) if drift else None, L.ptr(v), L.ptr(a), L.ptr(x_out), L.ptr(v_out), n, dim, code,
+                               float(self.dt), phase, snap_levels, L.ptr(buf.scalars), L.ptr(m),
+                               L.dtype_code(m), L.ptr(packed), L.stream_ptr(v.device)), "nb_kdk")
+        if emit_packed:
+            self._packed_key = self._packed_cache_key(x_out, m, packed)
+        return x_out, v_out
+
+    def step(self):
+        """One kick-drift-kick leapfrog tick (reference simulation.py:120-143)."""
+        stock_force = self._is_stock(self, "_compute_accelerations")
+        x, v, m, a = self._promoted_state(self.accelerations)
+        if stock_force:
+            x, v = self._kdk(L.KDK_KICK_DRIFT, x, v, a, m, emit_packed=True)
+            self.positions, self.velocities = x, v
+            packed = self._buf().bytes(f"packed{L.dtype_code(x)}", 0)
+            acc, snap_levels = self._accelerations_raw(x, m, packed)
+            # second half kick; int modes snap the fresh accelerations inside the same kernel
+            _, v = self._kdk(L.KDK_KICK, None, v, acc, m, snap_levels=snap_levels)
+            self.accelerations, self.velocities = acc, v
+        else:
+            x, v = self._kdk(L.KDK_KICK_DRIFT, x, v, a, m)
+            self.positions, self.velocities = x, v
+            acc = self._compute_accelerations()                       # user override (simulation.py:138)
+            self.accelerations = acc
+            x, v, m, a = self._promoted_state(acc)
+            _, v = self._kdk(L.KDK_KICK, None, v, a, m)
+            if x is not self.positions:
+                self.positions = x
+            self.velocities = v
+        self.tick += 1
+
+    def _run_fused(self, ticks: int):
+        """`ticks` stock ticks with the closing half kick of tick t fused into the opening of tick t+1."""
+        x, v, m, a = self._promoted_state(self.accelerations)
+        snap_levels = 0
+        pending = False                       # True: `a` still has to be applied as the closing half kick
+        for _ in range(ticks):
+            phase = L.KDK_KICK_KICK_DRIFT if pending else L.KDK_KICK_DRIFT
+            x, v = self._kdk(phase, x, v, a, m, snap_levels=snap_levels if pending else 0, emit_packed=True)
+            packed = self._buf().bytes(f"packed{L.dtype_code(x)}", 0)
+            a, snap_levels = self._accelerations_raw(x, m, packed)
+            if a.dtype != x.dtype:            # mode switched to FLOAT64 mid-run on fp32 state: promote once
+                x, v = x.to(a.dtype), v.to(a.dtype)
+                self._packed_key = None
+            pending = True
+            self.tick += 1
+        if pending:
+            _, v = self._kdk(L.KDK_KICK, None, v, a, m, snap_levels=snap_levels)
+        self.positions, self.velocities, self.accelerations = x, v, a
+
+    def run(self, num_ticks: int, callback: Callable = None, callback_interval: int = 100):
+        """Run `num_ticks` ticks; `callback(sim, sim.tick)` every `callback_interval` (simulation.py:145-158)."""
+        stock = self._is_stock(self, "step") and self._is_stock(self, "_compute_accelerations")
+        if not stock:
+            for t in range(num_ticks):
+                self.step()
+                if callback and (t + 1) % callback_interval == 0:
+                    callback(self, self.tick)
+            return
+        done = 0
+        while done < num_ticks:
+            if callback:
+                until_cb = callback_interval - (done % callback_interval)
+                span = min(until_cb, num_ticks - done)
+            else:
+                span = num_ticks - done
+            self._run_fused(span)
+            done += span
+            if callback and done % callback_interval == 0:
+                callback(self, self.tick)
+
+    # ------------------------------------------------------------------------------------------
+    # state and energies — reference simulation.py:160-196
+    # ------------------------------------------------------------------------------------------
+    def get_state(self) -> dict:
+        return {
+            "positions": self.positions.clone(),
+            "velocities": self.velocities.clone(),
+            "masses": self.masses.clone(),
+            "tick": self.tick,
+            "precision_mode": self.precision_mode.value,
+        }
+
+    @staticmethod
+    def _as_python_float(value: float, dtype: torch.dtype) -> float:
+        # the reference returns `.item()` of a tensor of this dtype
+        return float(np.float32(value)) if dtype == torch.float32 else float(value)
+
+    def get_kinetic_energy(self) -> float:
+        """0.5·Σ m v² (reference simulation.py:170-174)."""
+        _, v, m = self._state()
+        lib, buf = L.load(), self._buf()
+        n, dim = v.shape
+        out = torch.empty(1, dtype=torch.float64, device=v.device)
+        ws = buf.bytes("energy_ws", lib.nb_energy_workspace_bytes(n))
+        with torch.cuda.device(v.device):
+            L.check(lib.nb_kinetic_energy(L.ptr(v), L.ptr(m), n, dim, L.dtype_code(v), L.dtype_code(m), L.ptr(out),
+                                          L.ptr(ws), ws.numel(), L.stream_ptr(v.device)), "nb_kinetic_energy")
+        return self._as_python_float(0.5 * out.item(), torch.promote_types(v.dtype, m.dtype))
+
+    def get_potential_energy(self) -> float:
+        """−G·Σ_{i<j} m_i m_j / r_ij with softening (reference simulation.py:176-192)."""
+        x, _, m = self._state()
+        lib, buf = L.load(), self._buf()
+        n, dim = x.shape
+        packed = self._pack(x, m)
+        out = torch.empty(1, dtype=torch.float64, device=x.device)
+        ws = buf.bytes("energy_ws", lib.nb_energy_workspace_bytes(n))
+        with torch.cuda.device(x.device):
+            L.check(lib.nb_potential_energy(L.ptr(packed), n, L.ptr(x), L.ptr(m), n, dim, L.dtype_code(x),
+                                            L.dtype_code(m), float(self.softening_sq), L.ptr(out), L.ptr(ws),
+                                            ws.numel(), L.stream_ptr(x.device)), "nb_potential_energy")
+        # the kernel sums ordered pairs i != j: halve for i < j
+        return self._as_python_float(-float(self.G) * 0.5 * out.item(), torch.promote_types(x.dtype, m.dtype))
+
+    def get_total_energy(self) -> float:
+        return self.get_kinetic_energy() + self.get_potential_energy()
+
+
+def run_comparison(
+    positions: torch.Tensor,
+    velocities: torch.Tensor,
+    masses: torch.Tensor,
+    modes: list,
+    num_ticks: int = 1000,
+    callback: Callable = None,
+    callback_interval: int = 100,
+    **sim_kwargs,
+) -> dict:
+    """Same initial conditions under several precision modes (reference simulation.py:199-250)."""
+    results = {}
+    for mode in modes:
+        print(f"\nRunning simulation with {mode.value} precision...")
+        sim = GalaxySimulation(positions.clone(), velocities.clone(), masses.clone(), precision_mode=mode,
+                               **sim_kwargs)
+        history = {"positions": [positions.clone().cpu()], "energies": [sim.get_total_energy()], "ticks": [0]}
+
+        def record(s, tick, history=history):
+            history["positions"].append(s.positions.clone().cpu())
+            history["energies"].append(s.get_total_energy())
+            history["ticks"].append(tick)
+            if callback:
+                callback(s, tick)
+
+        sim.run(num_ticks, callback=record, callback_interval=callback_interval)
+        results[mode.value] = {"final_state": sim.get_state(), "history": history, "simulation": sim}
+    return results

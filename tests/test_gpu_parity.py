@@ -1,0 +1,282 @@
+"""Parity of the sm_100a path (through the C ABI / Python shell) against the golden fixtures recorded
+from the reference and against the CPU oracle on identical seeded inputs.  Needs a B200: `-m gpu`.
+
+Tolerances (BASELINE.json north_star / SURVEY.md §8c):
+  accelerations  per-particle ‖Δa‖₂/‖a_ref‖₂ ≤ 1e-5 (fp32-class modes), ≤ 1e-12 (float64)
+  grid indices   bit-exact given identical pre-snap values
+  energies       |ΔE| ≤ 3e-6·|E| (the reference's own fp32 Σ carries ~1e-6), drift curves see below
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_port as ora
+
+pytestmark = pytest.mark.gpu
+
+FLOAT_MODES = ["float32", "float16", "bfloat16"]
+ALL_MODES = list(ora.MODES)
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def T(a, dtype=None):
+    t = torch.from_numpy(np.asarray(a))
+    return t if dtype is None else t.to(dtype)
+
+
+def rel_rows(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float((np.linalg.norm(a - b, axis=-1) / np.linalg.norm(b, axis=-1)).max())
+
+
+def make_sim(g, mode, **kw):
+    import nbody_cosmological_simulation_b200 as nb
+    pm = nb.get_mode_from_string(mode)
+    return nb.GalaxySimulation(T(g["pos"]).to(dev()), T(g["vel"]).to(dev()), T(g["mass"]).to(dev()),
+                               precision_mode=pm, **kw)
+
+
+def test_library_loaded_and_device_is_blackwell():
+    from nbody_cosmological_simulation_b200 import _lib as L
+    import ctypes
+    sm, maj, mnr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    L.check(L.load().nb_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr)))
+    assert maj.value == 10 and sm.value >= 100
+    with open("/proc/self/maps") as f:
+        assert "libnbody_b200.so" in f.read()
+
+
+# ---------------------------------------------------------------------------------------------------
+# accelerations
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", FLOAT_MODES)
+def test_initial_accelerations_float_modes(golden, mode):
+    g = golden("disk256_modes")
+    sim = make_sim(g, mode)
+    assert sim.accelerations.dtype == torch.float32
+    assert rel_rows(sim.accelerations.cpu().numpy(), g[f"{mode}/acc0"]) <= 1e-5
+
+
+def test_initial_accelerations_float64_mode_on_fp32_state(golden):
+    # d² is formed in fp32 (reference rounding sequence) and only then widened: must match to 1e-12
+    g = golden("disk256_modes")
+    sim = make_sim(g, "float64")
+    assert sim.accelerations.dtype == torch.float64
+    assert rel_rows(sim.accelerations.cpu().numpy(), g["float64/acc0"]) <= 1e-12
+
+
+def test_fp64_state(golden):
+    g = golden("disk128_f64")
+    sim = make_sim(g, "float64")
+    assert rel_rows(sim.accelerations.cpu().numpy(), g["acc0"]) <= 1e-12
+    assert abs(sim.get_kinetic_energy() - float(g["ke0"])) <= 1e-13 * abs(float(g["ke0"]))
+    assert abs(sim.get_potential_energy() - float(g["pe0"])) <= 1e-12 * abs(float(g["pe0"]))
+    sim.run(10)
+    assert sim.positions.dtype == torch.float64
+    np.testing.assert_allclose(sim.positions.cpu().numpy(), g["pos10"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(sim.velocities.cpu().numpy(), g["vel10"], rtol=0, atol=1e-12)
+    assert rel_rows(sim.accelerations.cpu().numpy(), g["acc10"]) <= 1e-11
+    assert abs(sim.get_potential_energy() - float(g["pe10"])) <= 1e-12 * abs(float(g["pe10"]))
+
+
+@pytest.mark.parametrize("mode", ["float32", "float64", "float16", "bfloat16"])
+def test_box3d_nonuniform_masses(golden, mode):
+    g = golden("box3d_200")
+    kw = dict(G=float(g["G"]), softening=float(g["softening"]), dt=float(g["dt"]))
+    sim = make_sim(g, mode, **kw)
+    tol = 1e-12 if mode == "float64" else 1e-5
+    assert rel_rows(sim.accelerations.cpu().numpy(), g[f"{mode}/acc0"]) <= tol
+    assert abs(sim.get_kinetic_energy() - float(g[f"{mode}/ke0"])) <= 2e-6 * abs(float(g[f"{mode}/ke0"]))
+    assert abs(sim.get_potential_energy() - float(g[f"{mode}/pe0"])) <= 3e-6 * abs(float(g[f"{mode}/pe0"]))
+    sim.run(int(g["ticks"]))
+    ptol = 1e-11 if mode == "float64" else 2e-5
+    np.testing.assert_allclose(sim.positions.cpu().numpy(), g[f"{mode}/pos"], rtol=0, atol=ptol)
+    np.testing.assert_allclose(sim.velocities.cpu().numpy(), g[f"{mode}/vel"], rtol=0, atol=ptol)
+
+
+def test_int_modes_presnap_and_levels(golden):
+    """Log-grid modes: the pre-snap accelerations (level table path) against the reference's, N=64."""
+    import nbody_cosmological_simulation_b200 as nb
+    g = golden("int_intermediates64")
+    pos, mass = T(g["pos"]).to(dev()), T(g["mass"]).to(dev())
+    sim = nb.GalaxySimulation(pos, torch.zeros_like(pos), mass, precision_mode=nb.PrecisionMode.INT4_SIM)
+    x, _, m = sim._state()
+    pre, levels = sim._accelerations_raw(x, m, sim._pack(x, m))
+    assert levels == 16
+    assert rel_rows(pre.cpu().numpy(), g["int4_sim/acc_presnap"]) <= 1e-5
+    # the custom mode is the d² grid alone (no force snap): directly comparable
+    simc = nb.GalaxySimulation(pos, torch.zeros_like(pos), mass, precision_mode=nb.PrecisionMode.CUSTOM)
+    assert rel_rows(simc.accelerations.cpu().numpy(), g["custom/acc0"]) <= 1e-5
+
+
+@pytest.mark.parametrize("mode,levels", [("int4_sim", 16), ("int8_sim", 256)])
+def test_int_modes_snapped_accelerations(golden, mode, levels):
+    g = golden("disk256_modes")
+    sim = make_sim(g, mode)
+    a, ref = sim.accelerations.cpu().numpy(), g[f"{mode}/acc0"]
+    assert len(np.unique(a)) <= levels                      # x and y share one linear grid
+    step = (ref.max() - ref.min()) / (levels - 1)
+    exact = np.abs(a - ref) <= 1e-5 * np.abs(ref).max()
+    # a pre-snap value within rounding of k+½ may land on the neighbouring level; nothing else may differ
+    assert exact.mean() >= 0.99
+    assert (np.abs(a - ref)[~exact] <= step * 1.001).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+# trajectories, energies, rotation curve
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["float32", "float16", "bfloat16", "float64"])
+def test_twenty_ticks(golden, mode):
+    g = golden("disk256_modes")
+    sim = make_sim(g, mode)
+    ke, pe = [sim.get_kinetic_energy()], [sim.get_potential_energy()]
+    sim.run(20, callback=lambda s, t: (ke.append(s.get_kinetic_energy()), pe.append(s.get_potential_energy())),
+            callback_interval=10)
+    assert sim.tick == 20
+    want_dtype = torch.float64 if mode == "float64" else torch.float32
+    assert sim.positions.dtype == want_dtype and sim.velocities.dtype == want_dtype   # fp32 -> fp64 promotion
+    tol = 1e-11 if mode == "float64" else 2e-6
+    np.testing.assert_allclose(sim.positions.cpu().numpy(), g[f"{mode}/pos"], rtol=0, atol=tol * 20)
+    np.testing.assert_allclose(sim.velocities.cpu().numpy(), g[f"{mode}/vel"], rtol=0, atol=tol)
+    etol = 1e-12 if mode == "float64" else 3e-6
+    np.testing.assert_allclose(np.array(ke), g[f"{mode}/ke"], rtol=etol)
+    np.testing.assert_allclose(np.array(pe), g[f"{mode}/pe"], rtol=max(etol, 1e-7 if mode == "float64" else 0))
+
+
+def test_step_equals_fused_run(golden):
+    """step() (observable state every tick) and run() (closing kick fused into the next tick) are bit-identical."""
+    g = golden("disk256_modes")
+    for mode in ("float32", "int4_sim", "float64"):
+        a, b = make_sim(g, mode), make_sim(g, mode)
+        for _ in range(7):
+            a.step()
+        b.run(7)
+        assert torch.equal(a.positions, b.positions) and torch.equal(a.velocities, b.velocities), mode
+        assert torch.equal(a.accelerations, b.accelerations), mode
+
+
+def test_rotation_curve_and_metrics(golden):
+    import nbody_cosmological_simulation_b200 as nb
+    from nbody_cosmological_simulation_b200 import metrics as M
+    g = golden("disk256_modes")
+    pos, vel, mass = T(g["pos"]).to(dev()), T(g["vel"]).to(dev()), T(g["mass"]).to(dev())
+    rc = M.compute_rotation_curve(pos, vel)
+    np.testing.assert_array_equal(np.array(rc["num_stars_per_bin"]), g["init/rc_cnt"])      # membership exact
+    np.testing.assert_allclose(rc["radii"], g["init/rc_radii"], rtol=1e-6)
+    np.testing.assert_allclose(rc["velocities"], g["init/rc_vel"], rtol=1e-5, equal_nan=True)
+    assert sum(rc["num_stars_per_bin"]) == 255
+    rc7 = M.compute_rotation_curve(pos, vel, num_bins=7, max_radius=12.5)
+    np.testing.assert_array_equal(np.array(rc7["num_stars_per_bin"]), g["init/rc7_cnt"])
+    np.testing.assert_allclose(rc7["velocities"], g["init/rc7_vel"], rtol=1e-5, equal_nan=True)
+    assert abs(M.compute_galaxy_radius(pos, 90) - float(g["init/radius90"])) < 1e-5
+    assert abs(M.compute_bound_fraction(pos, vel, mass) - float(g["init/bound"])) < 1e-6
+    assert abs(M.compute_velocity_dispersion(vel) - float(g["init/dispersion"])) < 1e-6
+    g3 = golden("box3d_200")
+    rc3 = M.compute_rotation_curve(T(g3["pos"]).to(dev()), T(g3["vel"]).to(dev()), num_bins=10)
+    np.testing.assert_array_equal(np.array(rc3["num_stars_per_bin"]), g3["init/rc_cnt"])
+    np.testing.assert_allclose(rc3["velocities"], g3["init/rc_vel"], rtol=1e-5, equal_nan=True)
+    m = nb.SimulationMetrics()
+    sim = make_sim(g, "float32")
+    nb.collect_metrics(sim, 0, m)
+    assert m.ticks == [0] and len(m.rotation_curves) == 1
+    assert abs(m.total_energy[0] - (g["float32/ke"][0] + g["float32/pe"][0])) <= 3e-6 * abs(m.total_energy[0])
+
+
+@pytest.mark.parametrize("mode", ["float64", "float32", "bfloat16", "float16", "int8_sim", "int4_sim"])
+def test_energy_drift_curves(golden, mode):
+    """(E−E0)/|E0| every 20 ticks over 200 ticks against the reference's curve.
+
+    Tolerance: max(2e-6, 5 % of the reference's own |drift|) per sample — the reference's fp32 energy sum
+    itself carries ~1e-6 relative noise; int modes are compared after the same snaps.
+    """
+    g = golden("drift128")
+    sim = make_sim(g, mode)
+    e = [sim.get_total_energy()]
+    sim.run(int(g["ticks"]), callback=lambda s, t: e.append(s.get_total_energy()), callback_interval=int(g["interval"]))
+    e, ref = np.array(e), g[f"{mode}/energy"]
+    drift, rdrift = (e - e[0]) / abs(e[0]), (ref - ref[0]) / abs(ref[0])
+    tol = np.maximum(2e-6, 0.05 * np.abs(rdrift))
+    if mode in ("int4_sim", "int8_sim"):
+        tol = np.maximum(tol, 0.25 * np.abs(rdrift).max())      # a flipped force level shifts the whole curve
+    assert (np.abs(drift - rdrift) <= tol).all(), (drift, rdrift)
+
+
+# ---------------------------------------------------------------------------------------------------
+# free-standing quantisers through the C ABI
+# ---------------------------------------------------------------------------------------------------
+def test_quantisers(golden):
+    from nbody_cosmological_simulation_b200 import quantization as Q
+    g = golden("quantizers")
+    x, xp, const = T(g["x"]).to(dev()), T(g["xp"]).to(dev()), T(g["const"]).to(dev())
+    for levels in (16, 256, 64, 3):
+        # linear grid: sub/div/mul/round/mul/add are IEEE-exact on both sides -> bit parity
+        np.testing.assert_array_equal(Q._grid_quantize(x, levels).cpu().numpy(), g[f"grid/x/L{levels}"])
+        got = Q._grid_quantize_safe(xp, levels, 0.01).cpu().numpy()
+        np.testing.assert_allclose(got, g[f"safe/xp/L{levels}"], rtol=2e-6)      # log/exp differ by ulps CPU vs GPU
+        assert len(np.unique(got)) <= levels
+    np.testing.assert_array_equal(Q._grid_quantize(const, 16).cpu().numpy(), g["grid/const"])
+    np.testing.assert_array_equal(Q._grid_quantize_safe(const, 16).cpu().numpy(), g["safe/const"])
+    for mode in Q.PrecisionMode:
+        got = Q.quantize_distance_squared(xp, mode).cpu().numpy()
+        ref = g[f"qd2/{mode.value}"]
+        assert got.dtype == ref.dtype
+        np.testing.assert_allclose(got, ref, rtol=2e-6 if "int" in mode.value or mode.value == "custom" else 0)
+        gf = Q.quantize_force(x, mode).cpu().numpy()
+        np.testing.assert_array_equal(gf, g[f"qforce/{mode.value}"])
+    big = Q.quantize_distance_squared(T(g["qd2/float16_big_in"]).to(dev()), Q.PrecisionMode.FLOAT16).cpu().numpy()
+    np.testing.assert_array_equal(big, g["qd2/float16_big"])
+
+
+def test_level_indices_bit_exact_on_identical_presnap_values(golden):
+    from nbody_cosmological_simulation_b200 import quantization as Q
+    g = golden("int_intermediates64")
+    for levels in (16, 256, 64):
+        n = T(g[f"L{levels}/normalized"]).to(dev())
+        np.testing.assert_array_equal(Q.snap_index(n).cpu().numpy(), g[f"L{levels}/index"])
+    ties = torch.arange(0, 64, dtype=torch.float32) + 0.5                  # round-half-to-even, not half-up
+    np.testing.assert_array_equal(Q.snap_index(ties.to(dev())).cpu().numpy(), torch.round(ties).numpy().astype(np.int32))
+    # end to end on the same d² matrix: index from the CUDA logf path vs the CPU reference's
+    d2 = T(g["dist_sq"]).to(dev())
+    for levels in (16, 256, 64):
+        out, idx = Q._grid_quantize_safe(d2, levels, 0.01, return_index=True)
+        same = idx.cpu().numpy() == g[f"L{levels}/index"]
+        assert same.mean() >= 0.999          # only a logf ulp exactly on a k+½ boundary may differ
+        np.testing.assert_allclose(out.cpu().numpy()[same], g[f"L{levels}/result"][same], rtol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------------
+# larger sizes: sampled targets against the oracle, and size-independent properties
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,dim,mode", [(20000, 3, "float32"), (20000, 2, "float32"), (8192, 3, "float64"),
+                                         (5000, 2, "int4_sim"), (5000, 2, "float16")])
+def test_sampled_targets_against_oracle(n, dim, mode):
+    import nbody_cosmological_simulation_b200 as nb
+    if dim == 3:
+        pos, vel, mass = ora.uniform_box(n, seed=42, dim=3)
+    else:
+        torch.manual_seed(5)
+        pos, vel, mass = nb.create_disk_galaxy(n, device=torch.device("cpu"))
+    if mode == "float64":
+        pos, vel, mass = pos.double(), vel.double(), mass.double()
+    sim = nb.GalaxySimulation(pos.to(dev()), vel.to(dev()), mass.to(dev()), precision_mode=nb.get_mode_from_string(mode))
+    x, _, m = sim._state()
+    got, _ = sim._accelerations_raw(x, m, sim._pack(x, m))
+    rows = slice(n // 2 - 64, n // 2 + 64)
+    want = ora.accelerations_presnap(pos, mass, mode, 0.001, 0.1, row_chunk=None if n <= 8192 else 128, rows=rows)
+    tol = 1e-12 if mode == "float64" else 1e-5
+    assert rel_rows(got[rows].cpu().numpy(), want.numpy()) <= tol
+
+
+def test_momentum_conservation_at_one_million():
+    """Σ_i m_i a_i = 0 for pairwise-antisymmetric forces: a size-independent check at the benchmark size."""
+    import nbody_cosmological_simulation_b200 as nb
+    n = 1 << 20
+    pos, vel, mass = ora.uniform_box(n, seed=42, dim=3)
+    sim = nb.GalaxySimulation(pos.to(dev()), vel.to(dev()), mass.to(dev()), precision_mode=nb.PrecisionMode.FLOAT32)
+    a = sim.accelerations.double()
+    net = (a * sim.masses.double().unsqueeze(-1)).sum(dim=0).abs().max().item()
+    scale = (a.abs() * sim.masses.double().unsqueeze(-1)).sum(dim=0).max().item()
+    assert net <= 1e-6 * scale
