@@ -86,9 +86,11 @@ int64_t nb_num_chunks(int64_t n, int dtype);               /* ceil(n / nb_chunk_
 int64_t nb_packed_bytes(int64_t n, int dim, int dtype);    /* nb_num_chunks * nb_chunk_bytes  */
 
 /* Replaces the `pos.unsqueeze(0)` / `masses.unsqueeze(0)` operands of simulation.py:83,105,181-186.
- * pos: (n, dim) of `dtype`; mass: (n,) of `mass_dtype`; packed: nb_packed_bytes(n, dim, dtype). */
+ * pos: (n, dim) of `dtype`; mass: (n,) of `mass_dtype`; packed: nb_packed_bytes(n, dim, dtype).
+ * total_chunks = 0 writes nb_num_chunks(n) chunks; a larger value also fills whole padding chunks
+ * (equal-sized per-rank slices for the all-gather of an i-range-sharded run). */
 int nb_pack_sources(const void* pos, const void* mass, int64_t n, int dim, int dtype, int mass_dtype,
-                    void* packed, void* stream);
+                    void* packed, int64_t total_chunks, void* stream);
 
 /* ---- force evaluation: GalaxySimulation._compute_accelerations, simulation.py:74-118 ------- */
 /* Bytes of scratch nb_accel needs for n_targets targets (partial sums of the j-split). */
@@ -136,11 +138,12 @@ typedef enum NbKdkPhase {
 /* One HBM round trip of the state per tick.  mul and add are separately rounded (no FMA) and dt/2,
  * dt are cast to the state dtype first, exactly as torch does.  If snap_levels > 0 the acceleration
  * is first snapped to the linear grid (nb_snap_accelerations semantics) and written back to `acc`.
- * x_out/v_out may alias x_in/v_in.  If packed_out != NULL (phases with a drift) the packed source
- * record of every updated particle is emitted as well (mass: (n,) of mass_dtype). */
+ * x_out/v_out may alias x_in/v_in only when packed_out == NULL.  If packed_out != NULL (phases with a drift) the packed source
+ * record of every updated particle is emitted as well (mass: (n,) of mass_dtype; total_chunks as in
+ * nb_pack_sources).  x_out/v_out must not alias the inputs when packed_out is given. */
 int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_out, int64_t n, int dim,
            int dtype, double dt, int phase, int snap_levels, const int64_t* scalars,
-           const void* mass, int mass_dtype, void* packed_out, void* stream);
+           const void* mass, int mass_dtype, void* packed_out, int64_t total_chunks, void* stream);
 
 /* ---- energies: simulation.py:170-196 ------------------------------------------------------- */
 int64_t nb_energy_workspace_bytes(int64_t n_targets);

@@ -35,7 +35,7 @@ PROTOTYPES = {
     "nb_chunk_bytes": (c_int64, [c_int, c_int]),
     "nb_num_chunks": (c_int64, [c_int64, c_int]),
     "nb_packed_bytes": (c_int64, [c_int64, c_int, c_int]),
-    "nb_pack_sources": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
+    "nb_pack_sources": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, c_int64, _P]),
     "nb_accel_workspace_bytes": (c_int64, [c_int64, c_int]),
     "nb_max_dist_sq": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, c_double, _P, _P]),
     "nb_level_table_bytes": (c_int64, [c_int]),
@@ -43,7 +43,7 @@ PROTOTYPES = {
     "nb_accel": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_double, c_double, _P, c_int, _P, _P, _P,
                          c_int64, _P]),
     "nb_snap_accelerations": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
-    "nb_kdk": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_double, c_int, c_int, _P, _P, c_int, _P, _P]),
+    "nb_kdk": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_double, c_int, c_int, _P, _P, c_int, _P, c_int64, _P]),
     "nb_energy_workspace_bytes": (c_int64, [c_int64]),
     "nb_potential_energy": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_double, _P, _P, c_int64, _P]),
     "nb_kinetic_energy": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, _P, c_int64, _P]),

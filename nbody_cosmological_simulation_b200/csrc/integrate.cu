@@ -168,8 +168,10 @@ inline int grid_for(int64_t work_items, int threads) {
 }
 
 template <typename T, int DIM, typename TM>
-int launch_pack(const void* pos, const void* mass, int64_t n, void* packed, cudaStream_t st) {
-    const int64_t n_units = nb_num_chunks(n, sizeof(T) == 4 ? NB_F32 : NB_F64) * kChunkUnits;
+int launch_pack(const void* pos, const void* mass, int64_t n, void* packed, int64_t total_chunks, cudaStream_t st) {
+    const int64_t natural = nb_num_chunks(n, sizeof(T) == 4 ? NB_F32 : NB_F64);
+    if (total_chunks != 0 && total_chunks < natural) return NB_ERR_INVALID_ARGUMENT;
+    const int64_t n_units = (total_chunks ? total_chunks : natural) * kChunkUnits;
     pack_kernel<T, DIM, TM><<<grid_for(n_units, 256), 256, 0, st>>>((const T*)pos, (const TM*)mass, n, (char*)packed, n_units);
     NB_CUDA_LAUNCH_CHECK();
     return NB_OK;
@@ -177,10 +179,12 @@ int launch_pack(const void* pos, const void* mass, int64_t n, void* packed, cuda
 
 template <typename T, int DIM, typename TM, int PHASE>
 int launch_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_out, int64_t n, double dt,
-               int snap_levels, const int64_t* scalars, const void* mass, void* packed, cudaStream_t st) {
+               int snap_levels, const int64_t* scalars, const void* mass, void* packed, int64_t total_chunks, cudaStream_t st) {
     constexpr int UP = sizeof(T) == 4 ? 2 : 1;
-    // with packed output the padding units of the last chunk are written too
-    const int64_t n_units = packed ? nb_num_chunks(n, sizeof(T) == 4 ? NB_F32 : NB_F64) * kChunkUnits : (n + UP - 1) / UP;
+    // with packed output the padding units (rest of the last chunk, plus whole padding chunks) are written too
+    const int64_t natural = nb_num_chunks(n, sizeof(T) == 4 ? NB_F32 : NB_F64);
+    if (packed && total_chunks != 0 && total_chunks < natural) return NB_ERR_INVALID_ARGUMENT;
+    const int64_t n_units = packed ? (total_chunks ? total_chunks : natural) * kChunkUnits : (n + UP - 1) / UP;
     kdk_kernel<T, DIM, TM, PHASE><<<grid_for(n_units, 256), 256, 0, st>>>(
         (const T*)x_in, (const T*)v_in, (T*)acc, (T*)x_out, (T*)v_out, n, (T)(dt / 2), (T)dt, snap_levels, scalars,
         (const TM*)mass, (char*)packed, n_units);
@@ -193,11 +197,11 @@ int launch_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void*
 using namespace nb;
 
 extern "C" int nb_pack_sources(const void* pos, const void* mass, int64_t n, int dim, int dtype, int mass_dtype,
-                               void* packed, void* stream) {
+                               void* packed, int64_t total_chunks, void* stream) {
     if (!pos || !mass || !packed || n <= 0 || (dim != 2 && dim != 3)) return NB_ERR_INVALID_ARGUMENT;
     cudaStream_t st = (cudaStream_t)stream;
 #define NB_PACK_CASE(T, DT, TM, MDT, D) \
-    if (dtype == DT && mass_dtype == MDT && dim == D) return launch_pack<T, D, TM>(pos, mass, n, packed, st);
+    if (dtype == DT && mass_dtype == MDT && dim == D) return launch_pack<T, D, TM>(pos, mass, n, packed, total_chunks, st);
     NB_PACK_CASE(float, NB_F32, float, NB_F32, 2) NB_PACK_CASE(float, NB_F32, float, NB_F32, 3)
     NB_PACK_CASE(float, NB_F32, double, NB_F64, 2) NB_PACK_CASE(float, NB_F32, double, NB_F64, 3)
     NB_PACK_CASE(double, NB_F64, float, NB_F32, 2) NB_PACK_CASE(double, NB_F64, float, NB_F32, 3)
@@ -208,7 +212,7 @@ extern "C" int nb_pack_sources(const void* pos, const void* mass, int64_t n, int
 
 extern "C" int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_out, int64_t n, int dim, int dtype,
                       double dt, int phase, int snap_levels, const int64_t* scalars, const void* mass, int mass_dtype,
-                      void* packed_out, void* stream) {
+                      void* packed_out, int64_t total_chunks, void* stream) {
     if (!v_in || !acc || !v_out || n <= 0 || (dim != 2 && dim != 3)) return NB_ERR_INVALID_ARGUMENT;
     if (phase != NB_KDK_KICK && (!x_in || !x_out)) return NB_ERR_INVALID_ARGUMENT;
     if (snap_levels < 0 || snap_levels == 1 || (snap_levels > 0 && !scalars)) return NB_ERR_INVALID_ARGUMENT;
@@ -220,7 +224,7 @@ extern "C" int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out
     if (!mass) mass_dtype = dtype;
 #define NB_KDK_CASE(T, DT, TM, MDT, D, PH)                                  \
     if (dtype == DT && mass_dtype == MDT && dim == D && phase == PH)        \
-        return launch_kdk<T, D, TM, PH>(x_in, v_in, acc, x_out, v_out, n, dt, snap_levels, scalars, mass, packed_out, st);
+        return launch_kdk<T, D, TM, PH>(x_in, v_in, acc, x_out, v_out, n, dt, snap_levels, scalars, mass, packed_out, total_chunks, st);
 #define NB_KDK_PHASES(T, DT, TM, MDT, D) \
     NB_KDK_CASE(T, DT, TM, MDT, D, NB_KDK_KICK_DRIFT) NB_KDK_CASE(T, DT, TM, MDT, D, NB_KDK_KICK) NB_KDK_CASE(T, DT, TM, MDT, D, NB_KDK_KICK_KICK_DRIFT)
     NB_KDK_PHASES(float, NB_F32, float, NB_F32, 2) NB_KDK_PHASES(float, NB_F32, float, NB_F32, 3)

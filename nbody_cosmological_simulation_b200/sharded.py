@@ -1,0 +1,233 @@
+"""Multi-GPU all-pairs engine: targets sharded by i-range, sources all-gathered every tick.
+
+One process per GPU (`torch.distributed`, NCCL over NVLink 5 / NVSwitch).  Each rank owns the
+positions/velocities/accelerations of a contiguous, chunk-aligned slice of the particles
+(SURVEY.md §8e).  A tick is
+
+    fused KDK on the local slice           -> new local x, v  + the local PACKED source records
+    all_gather_into_tensor(packed)         -> full source set on every rank (N·16 B fp32, N·32 B fp64)
+    [int modes: local max d² -> all_reduce(MAX) -> level table]
+    force kernel: local targets × all sources
+    [INT8/INT4: all_reduce(MIN/MAX) of the local acceleration extrema -> shared snap grid]
+
+No other data-path collective exists; energies add one all_reduce(SUM) of a double.  The arithmetic
+per pair is the single-GPU kernel's, so results are identical to `GalaxySimulation` up to the
+documented Σ_j tolerance (they are bit-identical here: the j-order per target does not depend on P).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from .quantization import PrecisionMode, levels_for_mode
+
+_INT_FORCE_SNAP = {PrecisionMode.INT8_SIM: 256, PrecisionMode.INT4_SIM: 16}
+
+
+class ShardPlan:
+    """Chunk-aligned i-range partition of N particles over `world` ranks (pure host logic)."""
+
+    def __init__(self, n: int, world: int, chunk_sources: int):
+        if n <= 0 or world <= 0:
+            raise ValueError("n and world must be positive")
+        self.n, self.world, self.chunk_sources = int(n), int(world), int(chunk_sources)
+        total_chunks = -(-self.n // self.chunk_sources)
+        base, extra = divmod(total_chunks, self.world)
+        if base == 0:
+            raise ValueError(f"N={n} is too small to shard over {world} ranks: need at least one chunk of "
+                             f"{chunk_sources} particles per rank")
+        self.chunks = [base + (1 if r < extra else 0) for r in range(self.world)]
+        self.chunk_start = [sum(self.chunks[:r]) for r in range(self.world)]
+        self.start = [c * self.chunk_sources for c in self.chunk_start]
+        self.count = [min(self.n, (self.chunk_start[r] + self.chunks[r]) * self.chunk_sources) - self.start[r]
+                      for r in range(self.world)]
+        self.slot_chunks = base + (1 if extra else 0)          # equal-sized all-gather slot per rank
+        self.padded_sources = self.world * self.slot_chunks * self.chunk_sources
+        assert sum(self.count) == self.n and min(self.count) >= 1
+
+    def slice(self, rank: int) -> slice:
+        return slice(self.start[rank], self.start[rank] + self.count[rank])
+
+
+class ShardedGalaxySimulation:
+    """`GalaxySimulation` semantics on P ranks.  Every rank passes the same full initial arrays (same seed or
+    broadcast beforehand); `positions`/`velocities`/`accelerations`/`masses` hold the LOCAL slice."""
+
+    def __init__(self, positions: torch.Tensor, velocities: torch.Tensor, masses: torch.Tensor,
+                 precision_mode: PrecisionMode = PrecisionMode.FLOAT64, G: float = 0.001, softening: float = 0.1,
+                 dt: float = 0.01, device: torch.device = None, group=None, ops=None):
+        if ops is None:
+            from .ops import CudaOps
+            ops = CudaOps()
+        self.ops = ops
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.device(device) if device is not None else positions.device
+        self.precision_mode = precision_mode
+        self.G, self.softening, self.softening_sq, self.dt = G, softening, softening ** 2, dt
+        self.num_stars = len(masses)
+        self.dim = positions.shape[1]
+
+        # dtype of the state: FLOAT64 mode promotes fp32 state to fp64 after the first kick (Appendix A);
+        # the sharded engine applies that promotion up front for the integrator and keeps the fp32 copy
+        # for the very first force evaluation only.
+        self.plan = ShardPlan(self.num_stars, self.world, ops.chunk_sources(positions.dtype))
+        sl = self.plan.slice(self.rank)
+        self.positions = positions[sl].clone().to(self.device).contiguous()
+        self.velocities = velocities[sl].clone().to(self.device).contiguous()
+        self.masses = masses[sl].clone().to(self.device).contiguous()
+        self.scalars = ops.new_scalars(self.device)
+        self._packed_all = None
+        self.accelerations = self._force(self.positions, emit=True)
+        self._snap_now()
+        self.tick = 0
+
+    # ---- collectives ------------------------------------------------------------------------------
+    def _all_gather_packed(self, local_packed: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return local_packed
+        if self._packed_all is None or self._packed_all.numel() != local_packed.numel() * self.world:
+            self._packed_all = torch.empty(local_packed.numel() * self.world, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(self._packed_all, local_packed, group=self.group)
+        return self._packed_all
+
+    def _all_reduce(self, t: torch.Tensor, op):
+        if self.world > 1:
+            dist.all_reduce(t, op=op, group=self.group)
+
+    # ---- force ------------------------------------------------------------------------------------
+    def _plan_for(self, dtype) -> ShardPlan:
+        cs = self.ops.chunk_sources(dtype)
+        if cs != self.plan.chunk_sources:
+            # fp32 -> fp64 promotion halves the chunk size in particles; the slice boundaries stay valid
+            # because they are multiples of the fp32 chunk (256 = 2·128)
+            plan = ShardPlan.__new__(ShardPlan)
+            plan.__dict__.update(self.plan.__dict__)
+            plan.chunk_sources = cs
+            ratio = self.plan.chunk_sources // cs
+            plan.chunks = [c * ratio for c in self.plan.chunks]
+            plan.slot_chunks = self.plan.slot_chunks * ratio
+            return plan
+        return self.plan
+
+    def _local_packed_buffer(self, dtype) -> torch.Tensor:
+        plan = self._plan_for(dtype)
+        nbytes = plan.slot_chunks * self.ops.chunk_bytes(self.dim)
+        key = "_lp%d" % nbytes
+        buf = getattr(self, key, None)
+        if buf is None:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            setattr(self, key, buf)
+        return buf
+
+    def _force(self, x: torch.Tensor, emit: bool, local_packed: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Pre-snap accelerations of the local targets; `emit` packs x first (otherwise the KDK kernel already did)."""
+        ops, plan = self.ops, self._plan_for(x.dtype)
+        if emit:
+            local_packed = self._local_packed_buffer(x.dtype)
+            ops.pack(x, self.masses, local_packed, plan.slot_chunks)
+        packed = self._all_gather_packed(local_packed)
+        self._last_packed, self._last_nsrc = packed, plan.padded_sources if self.world > 1 else plan.slot_chunks * plan.chunk_sources
+        n_src = self._last_nsrc
+        mode = self.precision_mode
+        levels = levels_for_mode(mode) or 0
+        table = None
+        if levels:
+            ops.reset_scalars(self.scalars)
+            ops.max_dist_sq(packed, n_src, x, self.softening_sq, self.scalars)
+            self._all_reduce(self.scalars[L.SLOT_MAX_D2:L.SLOT_MAX_D2 + 1], dist.ReduceOp.MAX)
+            table = ops.build_level_table(self.scalars, x.dtype, self.softening_sq, 0.01, self.G, levels)
+        acc = ops.accel(packed, n_src, x, mode.value, self.G, self.softening_sq, table, levels, self.scalars)
+        if mode in _INT_FORCE_SNAP:
+            self._all_reduce(self.scalars[L.SLOT_ACC_MIN:L.SLOT_ACC_MIN + 1], dist.ReduceOp.MIN)
+            self._all_reduce(self.scalars[L.SLOT_ACC_MAX:L.SLOT_ACC_MAX + 1], dist.ReduceOp.MAX)
+        return acc
+
+    def _snap_now(self):
+        levels = _INT_FORCE_SNAP.get(self.precision_mode, 0)
+        if levels:
+            self.ops.snap(self.accelerations, levels, self.scalars)
+
+    # ---- integrator -------------------------------------------------------------------------------
+    def _promote(self):
+        dt = torch.promote_types(torch.promote_types(self.positions.dtype, self.velocities.dtype), self.accelerations.dtype)
+        return self.positions.to(dt), self.velocities.to(dt), self.accelerations.to(dt)
+
+    def _run_fused(self, ticks: int):
+        ops = self.ops
+        x, v, a = self._promote()
+        snap_levels, pending = 0, False
+        for _ in range(ticks):
+            phase = L.KDK_KICK_KICK_DRIFT if pending else L.KDK_KICK_DRIFT
+            plan = self._plan_for(x.dtype)
+            local_packed = self._local_packed_buffer(x.dtype)
+            x, v = ops.kdk(phase, x, v, a, self.masses, self.dt, snap_levels if pending else 0, self.scalars,
+                           packed=local_packed, total_chunks=plan.slot_chunks)
+            a = self._force(x, emit=False, local_packed=local_packed)
+            snap_levels = _INT_FORCE_SNAP.get(self.precision_mode, 0)
+            pending = True
+            self.tick += 1
+        if pending:
+            _, v = ops.kdk(L.KDK_KICK, None, v, a, self.masses, self.dt, snap_levels, self.scalars)
+        self.positions, self.velocities, self.accelerations = x, v, a
+
+    def step(self):
+        self._run_fused(1)
+
+    def run(self, num_ticks: int, callback: Callable = None, callback_interval: int = 100):
+        done = 0
+        while done < num_ticks:
+            span = num_ticks - done
+            if callback:
+                span = min(callback_interval - (done % callback_interval), span)
+            self._run_fused(span)
+            done += span
+            if callback and done % callback_interval == 0:
+                callback(self, self.tick)
+
+    # ---- energies / gathers -----------------------------------------------------------------------
+    def _sources_for(self, x):
+        plan = self._plan_for(x.dtype)
+        local_packed = self._local_packed_buffer(x.dtype)
+        self.ops.pack(x, self.masses, local_packed, plan.slot_chunks)
+        packed = self._all_gather_packed(local_packed)
+        n_src = plan.padded_sources if self.world > 1 else plan.slot_chunks * plan.chunk_sources
+        return packed, n_src
+
+    def get_kinetic_energy(self) -> float:
+        s = self.ops.kinetic(self.velocities.contiguous(), self.masses)
+        self._all_reduce(s, dist.ReduceOp.SUM)
+        val = 0.5 * s.item()
+        return float(np.float32(val)) if self.velocities.dtype == torch.float32 else float(val)
+
+    def get_potential_energy(self) -> float:
+        x = self.positions.contiguous()
+        packed, n_src = self._sources_for(x)
+        s = self.ops.potential(packed, n_src, x, self.masses, self.softening_sq)
+        self._all_reduce(s, dist.ReduceOp.SUM)
+        val = -float(self.G) * 0.5 * s.item()
+        return float(np.float32(val)) if x.dtype == torch.float32 else float(val)
+
+    def get_total_energy(self) -> float:
+        return self.get_kinetic_energy() + self.get_potential_energy()
+
+    def gather(self, local: torch.Tensor) -> torch.Tensor:
+        """Full (N, …) tensor from the local slices (variable slice sizes -> padded all_gather)."""
+        if self.world == 1:
+            return local.clone()
+        rows = max(self.plan.count)
+        pad = torch.zeros((rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+        out = torch.empty((self.world * rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, pad, group=self.group)
+        parts = [out[r * rows: r * rows + self.plan.count[r]] for r in range(self.world)]
+        return torch.cat(parts, dim=0)
+
+    def get_state(self) -> dict:
+        return {"positions": self.gather(self.positions), "velocities": self.gather(self.velocities),
+                "masses": self.gather(self.masses), "tick": self.tick, "precision_mode": self.precision_mode.value}

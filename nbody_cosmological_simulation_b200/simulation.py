@@ -108,7 +108,7 @@ class GalaxySimulation:
         key = self._packed_cache_key(x, m, packed)
         if getattr(self, "_packed_key", None) != key:
             with torch.cuda.device(x.device):
-                L.check(L.load().nb_pack_sources(L.ptr(x), L.ptr(m), n, dim, code, L.dtype_code(m), L.ptr(packed),
+                L.check(L.load().nb_pack_sources(L.ptr(x), L.ptr(m), n, dim, code, L.dtype_code(m), L.ptr(packed), 0,
                                                  L.stream_ptr(x.device)), "nb_pack_sources")
             self._packed_key = key
         return packed
@@ -184,7 +184,7 @@ class GalaxySimulation:
         with torch.cuda.device(v.device):
             L.check(lib.nb_kdk(L.ptr(x) if drift else None, L.ptr(v), L.ptr(a), L.ptr(x_out), L.ptr(v_out), n, dim, code,
                                float(self.dt), phase, snap_levels, L.ptr(buf.scalars), L.ptr(m),
-                               L.dtype_code(m), L.ptr(packed), L.stream_ptr(v.device)), "nb_kdk")
+                               L.dtype_code(m), L.ptr(packed), 0, L.stream_ptr(v.device)), "nb_kdk")
         if emit_packed:
             self._packed_key = self._packed_cache_key(x_out, m, packed)
         return x_out, v_out
