@@ -78,7 +78,11 @@ double nb_double_from_key(int64_t key);
  * The force / energy kernels stream sources from a chunk-major packed buffer that TMA bulk copies
  * (cp.async.bulk) move into shared memory.  One chunk = NB_CHUNK_UNITS units; a unit is two fp32
  * sources or one fp64 source (16 B of x,y + 16 B (D=3: z,m) or 8 B (D=2: m)).
- * Padding sources (mass 0, position of the last real source) fill the last chunk. */
+ * Padding records fill the last chunk (and whole padding chunks when total_chunks asks for them): mass 0
+ * and every coordinate = NB_PAD_COORD_F32 / NB_PAD_COORD_F64, far enough that d²^-3/2 underflows to exactly
+ * 0, so a pad adds nothing to any force, potential or max-d² result. */
+#define NB_PAD_COORD_F32 1.0e18f
+#define NB_PAD_COORD_F64 1.0e150
 #define NB_CHUNK_UNITS 128
 int64_t nb_chunk_sources(int dtype);                       /* 256 for NB_F32, 128 for NB_F64 */
 int64_t nb_chunk_bytes(int dim, int dtype);                /* 4096 (D=3) / 3072 (D=2)         */
@@ -119,9 +123,13 @@ int nb_build_level_table(const int64_t* scalars, int dtype, double eps_sq, doubl
  * Output dtype: NB_F64 when dtype==NB_F64 or mode==NB_MODE_FLOAT64 (torch promotion at
  * quantization.py:45), else NB_F32.  For INT8/INT4 this is the PRE-snap acceleration; the min/max
  * over all outputs is folded into scalars[NB_SLOT_ACC_MIN/MAX] (quantization.py:78-79) and the snap
- * itself is nb_snap_accelerations or fused into nb_kdk. */
+ * itself is nb_snap_accelerations or fused into nb_kdk.
+ * uniform_mass != 0 asserts that every real source has mass == mass_value (the caller has checked): the
+ * FLOAT32-on-fp32 and FLOAT64-on-fp64 kernels then drop the per-pair mass multiply (12 -> 11 packed fp32 ops,
+ * 16 -> 15 fp64 ops per pair) and scale by G·mass_value once per target; other modes ignore the hint. */
 int nb_accel(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt, int dim,
              int dtype, int mode, double G, double eps_sq, const void* level_table, int levels,
+             int uniform_mass, double mass_value,
              void* acc_out, int64_t* scalars, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* quantize_force -> _grid_quantize(a, levels) (simulation.py:115-116, quantization.py:74-88) with the
@@ -138,9 +146,8 @@ typedef enum NbKdkPhase {
 /* One HBM round trip of the state per tick.  mul and add are separately rounded (no FMA) and dt/2,
  * dt are cast to the state dtype first, exactly as torch does.  If snap_levels > 0 the acceleration
  * is first snapped to the linear grid (nb_snap_accelerations semantics) and written back to `acc`.
- * x_out/v_out may alias x_in/v_in only when packed_out == NULL.  If packed_out != NULL (phases with a drift) the packed source
- * record of every updated particle is emitted as well (mass: (n,) of mass_dtype; total_chunks as in
- * nb_pack_sources).  x_out/v_out must not alias the inputs when packed_out is given. */
+ * x_out/v_out may alias x_in/v_in.  If packed_out != NULL (phases with a drift) the packed source record of
+ * every updated particle is emitted as well (mass: (n,) of mass_dtype; total_chunks as in nb_pack_sources). */
 int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_out, int64_t n, int dim,
            int dtype, double dt, int phase, int snap_levels, const int64_t* scalars,
            const void* mass, int mass_dtype, void* packed_out, int64_t total_chunks, void* stream);

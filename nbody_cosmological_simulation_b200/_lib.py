@@ -40,8 +40,8 @@ PROTOTYPES = {
     "nb_max_dist_sq": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, c_double, _P, _P]),
     "nb_level_table_bytes": (c_int64, [c_int]),
     "nb_build_level_table": (c_int, [_P, c_int, c_double, c_double, c_double, c_int, _P, _P]),
-    "nb_accel": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_double, c_double, _P, c_int, _P, _P, _P,
-                         c_int64, _P]),
+    "nb_accel": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_double, c_double, _P, c_int, c_int, c_double,
+                         _P, _P, _P, c_int64, _P]),
     "nb_snap_accelerations": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     "nb_kdk": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_double, c_int, c_int, _P, _P, c_int, _P, c_int64, _P]),
     "nb_energy_workspace_bytes": (c_int64, [c_int64]),
@@ -105,6 +105,23 @@ def require_cuda(*tensors: torch.Tensor):
             raise NbodyLibraryError(
                 "nbody_cosmological_simulation_b200 runs on CUDA devices only (B200, sm_100a); got a tensor on "
                 f"'{t.device}'. There is deliberately no CPU fallback.")
+
+
+_uniform_cache = {}
+
+
+def uniform_mass(m: torch.Tensor):
+    """(is_uniform, value) for a mass tensor; one device->host read per distinct (tensor, version), then cached."""
+    key = (m.data_ptr(), m._version, m.numel(), m.dtype)
+    hit = _uniform_cache.get(key)
+    if hit is None:
+        if len(_uniform_cache) > 64:
+            _uniform_cache.clear()
+        lo, hi = torch.aminmax(m)
+        lo, hi = lo.item(), hi.item()
+        hit = (lo == hi, float(lo))
+        _uniform_cache[key] = hit
+    return hit
 
 
 def ptr(t):

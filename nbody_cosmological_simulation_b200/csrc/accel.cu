@@ -35,7 +35,9 @@ struct LevelHeader { float lo2, scale, min_val, degenerate; };
 // ======================================================================================================
 // fp32 state, packed-pair arithmetic
 // ======================================================================================================
-template <int DIM_, int QMODE, int IPT, int THREADS_>
+// UNI: all source masses are equal (checked by the caller): the per-pair `·m_j` is dropped and the common mass is
+// applied once per target in the finalize pass; padding records then rely on their far-away position (w == 0).
+template <int DIM_, int QMODE, int IPT, int THREADS_, bool UNI = false>
 struct ForceF32 {
     static constexpr int DIM = DIM_;
     static constexpr int THREADS = THREADS_;
@@ -129,7 +131,8 @@ struct ForceF32 {
                         d2 = __bfloat1622float2(h);
                     }
                     const float2 r = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
-                    w = mul2(mul2(r, r), mul2(r, ms));          // m_j / d²^1.5             simulation.py:97-105
+                    if (UNI) w = mul2(mul2(r, r), r);           // 1 / d²^1.5 (common mass applied in finalize)
+                    else w = mul2(mul2(r, r), mul2(r, ms));     // m_j / d²^1.5             simulation.py:97-105
                 }
                 ax[t] = fma2(w, dx, ax[t]);                     // Σ_j w·diff               simulation.py:112
                 ay[t] = fma2(w, dy, ay[t]);
@@ -174,7 +177,16 @@ __device__ __forceinline__ double mass_over_dist_cubed(double d2, double m) {
     return fma(w, ce, w);
 }
 
-template <int DIM_, int QMODE, int IPT, int THREADS_>
+__device__ __forceinline__ double inv_dist_cubed(double d2) {     // mass_over_dist_cubed with m == 1: one DMUL less
+    const double y0 = rsqrt64h(d2);
+    const double t = y0 * y0;
+    const double e = fma(-d2, t, 1.0);
+    const double ce = fma(1.875, e, 1.5) * e;
+    const double w = y0 * t;
+    return fma(w, ce, w);
+}
+
+template <int DIM_, int QMODE, int IPT, int THREADS_, bool UNI = false>
 struct ForceF64 {
     static constexpr int DIM = DIM_;
     static constexpr int THREADS = THREADS_;
@@ -210,7 +222,7 @@ struct ForceF64 {
                 if (DIM == 3) d2 = fma(dz, dz, d2);
                 double w;
                 if (QMODE == Q_F64) {
-                    w = mass_over_dist_cubed(d2, m);
+                    w = UNI ? inv_dist_cubed(d2) : mass_over_dist_cubed(d2, m);
                 } else {
                     float u = (float)d2;                                         // dist_sq.float()
                     if (QMODE == Q_F16) u = __half2float(__float2half_rn(u));
@@ -352,27 +364,9 @@ __global__ void __launch_bounds__(256) accel_finalize_kernel(const double* __res
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
-struct SplitPlan { int blocks_i; int splits; int chunks_per_split; };
-
-inline SplitPlan plan_splits(int64_t n_tgt, int64_t n_chunks, int targets_per_block, int max_splits_by_ws) {
-    SplitPlan p;
-    p.blocks_i = (int)((n_tgt + targets_per_block - 1) / targets_per_block);
-    // enough CTAs for ~12 per SM so that the tail (partial last wave) stays below a few percent
-    const int64_t want = (int64_t)kNumSMsB200 * 12;
-    int64_t s = (want + p.blocks_i - 1) / p.blocks_i;
-    if (s > n_chunks) s = n_chunks;
-    if (s > max_splits_by_ws) s = max_splits_by_ws;
-    if (s > 65535) s = 65535;
-    if (s < 1) s = 1;
-    p.chunks_per_split = (int)((n_chunks + s - 1) / s);
-    p.splits = (int)((n_chunks + p.chunks_per_split - 1) / p.chunks_per_split);
-    return p;
-}
-
 constexpr int kForceThreads = 256;
 constexpr int kForceIPT = 2;
 constexpr int kTargetsPerBlock = kForceThreads * kForceIPT;
-constexpr int kMaxSplits = 64;
 
 template <class Consumer, bool USE_LUT>
 int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, int* splits_out) {
@@ -380,14 +374,18 @@ int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, 
     const int64_t per_split = a.n_tgt * Consumer::DIM * (int64_t)sizeof(double);
     int64_t max_by_ws = workspace_bytes / per_split;
     if (max_by_ws < 1) return NB_ERR_WORKSPACE_TOO_SMALL;
-    if (max_by_ws > kMaxSplits) max_by_ws = kMaxSplits;
-    const SplitPlan p = plan_splits(a.n_tgt, a.n_chunks, Consumer::THREADS * kForceIPT, (int)max_by_ws);
-    a.chunks_per_split = p.chunks_per_split;
+    const int cap = max_splits_for(a.n_tgt, Consumer::DIM);
+    if (max_by_ws > cap) max_by_ws = cap;
     int smem = stream_smem_bytes(Consumer::DIM);
     if (USE_LUT) smem += (a.levels + 1) * 16;
     auto kern = accel_kernel<Consumer, USE_LUT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_status(e);
+    int ctas_per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, Consumer::THREADS + 32, smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    const SplitPlan p = plan_splits(a.n_tgt, a.n_chunks, Consumer::THREADS * kForceIPT, ctas_per_sm, (int)max_by_ws);
+    a.chunks_per_split = p.chunks_per_split;
     kern<<<dim3(p.blocks_i, p.splits), Consumer::THREADS + 32, smem, st>>>(a);
     NB_CUDA_LAUNCH_CHECK();
     *splits_out = p.splits;
@@ -401,15 +399,12 @@ using namespace nb;
 extern "C" int64_t nb_accel_workspace_bytes(int64_t n_targets, int dim) {
     if (n_targets <= 0 || (dim != 2 && dim != 3)) return 0;
     // room for the largest j-split the planner may choose for this many targets
-    const int blocks_i = (int)((n_targets + kTargetsPerBlock - 1) / kTargetsPerBlock);
-    int64_t s = ((int64_t)kNumSMsB200 * 12 + blocks_i - 1) / blocks_i;
-    if (s > kMaxSplits) s = kMaxSplits;
-    if (s < 1) s = 1;
-    return s * n_targets * dim * (int64_t)sizeof(double);
+    return (int64_t)max_splits_for(n_targets, dim) * n_targets * dim * (int64_t)sizeof(double);
 }
 
 extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt, int dim, int dtype,
-                        int mode, double G, double eps_sq, const void* level_table, int levels, void* acc_out,
+                        int mode, double G, double eps_sq, const void* level_table, int levels, int uniform_mass,
+                        double mass_value, void* acc_out,
                         int64_t* scalars, void* workspace, int64_t workspace_bytes, void* stream) {
     if (!packed_src || !pos_tgt || !acc_out || !workspace || n_src <= 0 || n_tgt <= 0 || (dim != 2 && dim != 3))
         return NB_ERR_INVALID_ARGUMENT;
@@ -433,18 +428,26 @@ extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_t
 
     int splits = 0, rc = NB_ERR_INVALID_ARGUMENT;
     constexpr int TH = kForceThreads, IPT = kForceIPT;
+    // uniform-mass fast path exists for the two headline kernels (fp32 state/FLOAT32, fp64 state/FLOAT64)
+    const bool uni = uniform_mass != 0 && ((dtype == NB_F32 && mode == NB_MODE_FLOAT32) || (dtype == NB_F64 && mode == NB_MODE_FLOAT64));
 #define NB_F32_CASE(D, Q, LUT) rc = launch_accel<ForceF32<D, Q, IPT, TH>, LUT>(a, workspace_bytes, st, &splits)
 #define NB_F64_CASE(D, Q) rc = launch_accel<ForceF64<D, Q, IPT, TH>, false>(a, workspace_bytes, st, &splits)
     if (dtype == NB_F32) {
         if (mode == NB_MODE_FLOAT64) {
             if (dim == 2) rc = launch_accel<ForceMixed<2, IPT, TH>, false>(a, workspace_bytes, st, &splits);
             else rc = launch_accel<ForceMixed<3, IPT, TH>, false>(a, workspace_bytes, st, &splits);
+        } else if (mode == NB_MODE_FLOAT32 && uni) {
+            if (dim == 2) rc = launch_accel<ForceF32<2, Q_F32, IPT, TH, true>, false>(a, workspace_bytes, st, &splits);
+            else rc = launch_accel<ForceF32<3, Q_F32, IPT, TH, true>, false>(a, workspace_bytes, st, &splits);
         } else if (mode == NB_MODE_FLOAT32) { if (dim == 2) NB_F32_CASE(2, Q_F32, false); else NB_F32_CASE(3, Q_F32, false); }
         else if (mode == NB_MODE_FLOAT16) { if (dim == 2) NB_F32_CASE(2, Q_F16, false); else NB_F32_CASE(3, Q_F16, false); }
         else if (mode == NB_MODE_BFLOAT16) { if (dim == 2) NB_F32_CASE(2, Q_BF16, false); else NB_F32_CASE(3, Q_BF16, false); }
         else { if (dim == 2) NB_F32_CASE(2, Q_LUT, true); else NB_F32_CASE(3, Q_LUT, true); }
     } else {
-        if (mode == NB_MODE_FLOAT64) { if (dim == 2) NB_F64_CASE(2, Q_F64); else NB_F64_CASE(3, Q_F64); }
+        if (mode == NB_MODE_FLOAT64 && uni) {
+            if (dim == 2) rc = launch_accel<ForceF64<2, Q_F64, IPT, TH, true>, false>(a, workspace_bytes, st, &splits);
+            else rc = launch_accel<ForceF64<3, Q_F64, IPT, TH, true>, false>(a, workspace_bytes, st, &splits);
+        } else if (mode == NB_MODE_FLOAT64) { if (dim == 2) NB_F64_CASE(2, Q_F64); else NB_F64_CASE(3, Q_F64); }
         else if (mode == NB_MODE_FLOAT32) { if (dim == 2) NB_F64_CASE(2, Q_F32); else NB_F64_CASE(3, Q_F32); }
         else if (mode == NB_MODE_FLOAT16) { if (dim == 2) NB_F64_CASE(2, Q_F16); else NB_F64_CASE(3, Q_F16); }
         else if (mode == NB_MODE_BFLOAT16) { if (dim == 2) NB_F64_CASE(2, Q_BF16); else NB_F64_CASE(3, Q_BF16); }
@@ -456,7 +459,7 @@ extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_t
     // finalize: Σ splits, ×G (float modes: G was hoisted out of the pair loop; LUT factors already carry G)
     const bool out_f64 = dtype == NB_F64 || mode == NB_MODE_FLOAT64;
     const bool minmax = mode == NB_MODE_INT8_SIM || mode == NB_MODE_INT4_SIM;
-    const double scale = lut ? 1.0 : G;
+    const double scale = lut ? 1.0 : (uni ? G * mass_value : G);
     const int64_t count = n_tgt * dim;
     int64_t blocks = (count + 255) / 256;
     if (blocks > kNumSMsB200 * 8) blocks = kNumSMsB200 * 8;

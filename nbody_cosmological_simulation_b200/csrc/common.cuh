@@ -15,6 +15,13 @@ constexpr int kNumSMsB200 = 148;
 constexpr int kChunkUnits = NB_CHUNK_UNITS;           // 128 units / chunk
 constexpr int kChunkABytes = kChunkUnits * 16;        // {x0,x1,y0,y1} (fp32 pair) or {x,y} (fp64)
 
+// Padding records (fill of the last chunk / whole padding chunks): mass 0 and a far-away position, chosen so
+// that d2^-3/2 underflows to exactly 0 in the state dtype: a pad contributes 0 force even in the kernels that
+// do not read per-source masses (uniform-mass fast path), and 0 potential because its mass is 0.
+constexpr float kPadCoordF32 = 1.0e18f;                // d² ~ 3e36 (finite); r³ ~ 2e-55 -> 0
+constexpr double kPadCoordF64 = 1.0e150;               // d² ~ 3e300 (finite); r³ ~ 2e-451 -> 0
+constexpr float kPadDetectF32 = 2.5e17f;               // |x| above this marks a pad (max-d² pass skips it)
+
 __host__ __device__ inline int chunk_b_bytes(int dim) { return kChunkUnits * (dim == 3 ? 16 : 8); }
 __host__ __device__ inline int chunk_bytes(int dim) { return kChunkABytes + chunk_b_bytes(dim); }
 __host__ __device__ inline int chunk_sources(int dtype) { return dtype == NB_F32 ? 2 * kChunkUnits : kChunkUnits; }

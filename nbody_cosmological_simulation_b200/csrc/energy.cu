@@ -238,9 +238,7 @@ extern "C" int64_t nb_energy_workspace_bytes(int64_t n_targets) {
     if (n_targets <= 0) return 0;
     // one double per CTA of the largest grid the planners below can choose
     const int64_t blocks_i = (n_targets + 511) / 512;
-    int64_t s = ((int64_t)kNumSMsB200 * 12 + blocks_i - 1) / blocks_i;
-    if (s < 1) s = 1;
-    int64_t ctas = blocks_i * s;
+    int64_t ctas = blocks_i * 64;                          // planner cap: 64 splits
     if (ctas < kNumSMsB200 * 16) ctas = kNumSMsB200 * 16;
     return ctas * (int64_t)sizeof(double);
 }
@@ -250,13 +248,8 @@ static int launch_potential(const void* packed_src, int64_t n_src, const void* p
                             int dtype, double eps_sq, double* out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
     constexpr int TH = 256, IPT = 2;
     const int64_t n_chunks = nb_num_chunks(n_src, dtype);
-    const int blocks_i = (int)((n_tgt + TH * IPT - 1) / (TH * IPT));
-    int64_t s = ((int64_t)kNumSMsB200 * 12 + blocks_i - 1) / blocks_i;
-    if (s > n_chunks) s = n_chunks;
-    if (s > 65535) s = 65535;
-    if (s < 1) s = 1;
-    const int cps = (int)((n_chunks + s - 1) / s);
-    const int splits = (int)((n_chunks + cps - 1) / cps);
+    const SplitPlan sp = plan_splits(n_tgt, n_chunks, TH * IPT, 3, 64);
+    const int blocks_i = sp.blocks_i, cps = sp.chunks_per_split, splits = sp.splits;
     const int64_t ctas = (int64_t)blocks_i * splits;
     if (workspace_bytes < ctas * (int64_t)sizeof(double)) return NB_ERR_WORKSPACE_TOO_SMALL;
     auto k = potential_kernel<T, TM, DIM, IPT, TH>;

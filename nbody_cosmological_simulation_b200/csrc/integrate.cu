@@ -75,10 +75,10 @@ __global__ void __launch_bounds__(256) pack_kernel(const T* __restrict__ pos, co
         for (int h = 0; h < UP; ++h) {
             int64_t i = unit * UP + h;
             bool real = i < n;
-            int64_t src = real ? i : n - 1;          // padding: position of the last real source, mass 0
+            const T far = sizeof(T) == 4 ? (T)kPadCoordF32 : (T)kPadCoordF64;     // padding record: far away, mass 0
 #pragma unroll
-            for (int k = 0; k < DIM; ++k) p[h][k] = pos[src * DIM + k];
-            m[h] = real ? (T)mass[src] : (T)0;
+            for (int k = 0; k < DIM; ++k) p[h][k] = real ? pos[i * DIM + k] : far;
+            m[h] = real ? (T)mass[i] : (T)0;
         }
         if constexpr (sizeof(T) == 4) emit_unit_f32<DIM>(packed, unit, p[0], p[UP - 1], m[0], m[UP - 1]);
         else emit_unit_f64<DIM>(packed, unit, p[0], m[0]);
@@ -123,24 +123,13 @@ __global__ void __launch_bounds__(256) kdk_kernel(const T* __restrict__ x_in, co
             }
         }
         if (PHASE != NB_KDK_KICK && packed) {
-            // padding half of the last unit / padding units of the last chunk
+            // padding half of the last unit / padding units of the last chunk(s): far away, mass 0
+            const T far = sizeof(T) == 4 ? (T)kPadCoordF32 : (T)kPadCoordF64;
 #pragma unroll
             for (int h = 0; h < UP; ++h) {
-                const int64_t i = unit * UP + h;
-                if (i >= n) {
-                    // position of the last real particle after its own update: recompute it here (cheap, rare)
-                    const int64_t s = n - 1;
+                if (unit * UP + h >= n) {
 #pragma unroll
-                    for (int k = 0; k < DIM; ++k) {
-                        const int64_t e = s * DIM + k;
-                        T a = acc[e];
-                        if (snap) a = grid.snap(a);
-                        T v = v_in[e];
-                        const T kick = mul_rn(a, half_dt);
-                        v = add_rn(v, kick);
-                        if (PHASE == NB_KDK_KICK_KICK_DRIFT) v = add_rn(v, kick);
-                        px[h][k] = add_rn(x_in[e], mul_rn(v, dt));
-                    }
+                    for (int k = 0; k < DIM; ++k) px[h][k] = far;
                     pm[h] = (T)0;
                 }
             }
@@ -218,8 +207,6 @@ extern "C" int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out
     if (snap_levels < 0 || snap_levels == 1 || (snap_levels > 0 && !scalars)) return NB_ERR_INVALID_ARGUMENT;
     if (packed_out && (!mass || phase == NB_KDK_KICK)) return NB_ERR_INVALID_ARGUMENT;
     if (!scalars) return NB_ERR_INVALID_ARGUMENT;       // the snap grid constructor always reads the block
-    // padding records re-derive the last particle's new position from x_in: never run in place then
-    if (packed_out && (x_out == x_in || v_out == v_in)) return NB_ERR_INVALID_ARGUMENT;
     cudaStream_t st = (cudaStream_t)stream;
     if (!mass) mass_dtype = dtype;
 #define NB_KDK_CASE(T, DT, TM, MDT, D, PH)                                  \

@@ -61,7 +61,10 @@ struct MaxDistF32 {
 #pragma unroll 4
         for (int p = 0; p < kChunkUnits; ++p) {
             const float4 a = A[p];
-            const float2 xs = make_float2(a.x, a.y), ys = make_float2(a.z, a.w);
+            // padding records sit at kPadCoordF32: turn them into NaN so that fmaxf() below ignores their pairs
+            const float nan = __int_as_float(0x7fffffff);
+            const float2 xs = make_float2(a.x > kPadDetectF32 ? nan : a.x, a.y > kPadDetectF32 ? nan : a.y);
+            const float2 ys = make_float2(a.z, a.w);
             float2 zs = make_float2(0.f, 0.f);
             if (DIM == 3) { const float4 b = B4[p]; zs = make_float2(b.x, b.y); }
 #pragma unroll
@@ -252,13 +255,9 @@ extern "C" int nb_max_dist_sq(const void* packed_src, int64_t n_src, const void*
     if (dtype != NB_F32) return NB_ERR_UNSUPPORTED;       // int modes on fp64 state: no caller in the reference
     constexpr int TH = 256, IPT = 2;
     const int64_t n_chunks = nb_num_chunks(n_src, dtype);
-    const int blocks_i = (int)((n_tgt + TH * IPT - 1) / (TH * IPT));
-    int64_t s = ((int64_t)kNumSMsB200 * 12 + blocks_i - 1) / blocks_i;
-    if (s > n_chunks) s = n_chunks;
-    if (s > 65535) s = 65535;
-    if (s < 1) s = 1;
-    const int cps = (int)((n_chunks + s - 1) / s);
-    const int splits = (int)((n_chunks + cps - 1) / cps);
+    // 3 CTAs/SM is what the register budget of these kernels allows; exact occupancy matters little here
+    const SplitPlan sp = plan_splits(n_tgt, n_chunks, TH * IPT, 3, 64);
+    const int blocks_i = sp.blocks_i, cps = sp.chunks_per_split, splits = sp.splits;
     cudaStream_t st = (cudaStream_t)stream;
     const int smem = stream_smem_bytes(dim);
     if (dim == 2) {

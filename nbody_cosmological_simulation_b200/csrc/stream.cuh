@@ -6,6 +6,7 @@
 // LDS.128 reads and release it through an "empty" mbarrier.  Warps may drift apart by up to
 // kStages-1 stages, so there is no CTA-wide barrier in the steady state.
 #pragma once
+#include <math.h>
 #include "common.cuh"
 
 namespace nb {
@@ -15,6 +16,52 @@ constexpr int kStageChunks = 4;                 // 16 KB (D=3) / 12 KB (D=2) per
 constexpr int kBarrierBytes = 128;              // full[kStages] + empty[kStages] mbarriers, padded
 
 __host__ __device__ inline int stream_smem_bytes(int dim) { return kBarrierBytes + kStages * kStageChunks * chunk_bytes(dim); }
+
+// ---- j-split planning (host) ------------------------------------------------------------------------
+// grid = (blocks_i target blocks) x (splits source ranges).  All CTAs of a launch cost about the same, so
+// the makespan is ceil(CTAs / resident slots) waves: pick the split count that wastes the least of the
+// last wave, charging a small fixed cost per CTA (pipeline fill, target load, partial-sum store).
+struct SplitPlan { int blocks_i; int splits; int chunks_per_split; };
+
+inline int device_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = kNumSMsB200;
+        cudaGetLastError();
+    }
+    return sms;
+}
+
+inline SplitPlan plan_splits(int64_t n_tgt, int64_t n_chunks, int targets_per_block, int ctas_per_sm, int max_splits) {
+    SplitPlan best{};
+    best.blocks_i = (int)((n_tgt + targets_per_block - 1) / targets_per_block);
+    const double slots = (double)device_sm_count() * (ctas_per_sm > 0 ? ctas_per_sm : 1);
+    if (max_splits > 65535) max_splits = 65535;
+    double best_eff = -1.0;
+    for (int64_t s = 1; s <= max_splits && s <= n_chunks; ++s) {
+        const int64_t cps = (n_chunks + s - 1) / s;
+        const int64_t splits = (n_chunks + cps - 1) / cps;
+        if (splits != s) continue;                              // same plan as a smaller s
+        const double ctas = (double)best.blocks_i * (double)splits;
+        const double waves = ceil(ctas / slots);
+        // useful work / capacity of the waves, each CTA paying ~0.2 chunk-equivalents of fixed cost
+        const double eff = ((double)best.blocks_i * (double)n_chunks) / (waves * slots * ((double)cps + 0.2));
+        if (eff > best_eff * 1.01) { best_eff = eff; best.splits = (int)splits; best.chunks_per_split = (int)cps; }
+    }
+    if (best_eff < 0) { best.splits = 1; best.chunks_per_split = (int)n_chunks; }
+    return best;
+}
+
+// upper bound on the split count used for sizing workspaces (<= 256 MiB of partial sums, <= 32 splits)
+inline int max_splits_for(int64_t n_tgt, int dim) {
+    const int64_t per_split = n_tgt * dim * (int64_t)sizeof(double);
+    int64_t s = ((int64_t)256 << 20) / (per_split > 0 ? per_split : 1);
+    if (s > 32) s = 32;
+    if (s < 1) s = 1;
+    return (int)s;
+}
 
 // Consumer concept:
 //   static constexpr int DIM, THREADS (consumer threads; the CTA has THREADS + 32);
@@ -46,7 +93,11 @@ __device__ __forceinline__ void stream_sources(const char* __restrict__ src, int
         if (lane == 0) {
             for (int it = 0; it < n_iters; ++it) {
                 const int s = it % kStages;
-                if (it >= kStages) mbar_wait(bar0 + 8 * (kStages + s), ((it / kStages) - 1) & 1);
+                if (it >= kStages) {
+                    // the producer has ~a stage of compute time to spare: back off instead of spinning on the
+                    // issue port of its SMSP (ncu: the bare try_wait loop was 19 % of all executed instructions)
+                    while (!mbar_try_wait(bar0 + 8 * (kStages + s), ((it / kStages) - 1) & 1)) __nanosleep(256);
+                }
                 const int first = it * kStageChunks;
                 const int cnt = min(kStageChunks, n_chunks - first);
                 const uint32_t bytes = (uint32_t)(cnt * cb);

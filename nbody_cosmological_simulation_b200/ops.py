@@ -82,7 +82,7 @@ class CudaOps:
                     "nb_build_level_table")
         return table
 
-    def accel(self, packed, n_src, x_tgt, mode: str, G, eps_sq, table, levels, scalars):
+    def accel(self, packed, n_src, x_tgt, mode: str, G, eps_sq, table, levels, scalars, uniform=(False, 0.0)):
         L.require_cuda(packed, x_tgt, scalars)
         n, dim = x_tgt.shape
         code = L.dtype_code(x_tgt)
@@ -91,7 +91,8 @@ class CudaOps:
         ws = self._scratch("accel", self.lib.nb_accel_workspace_bytes(n, dim), x_tgt.device)
         with torch.cuda.device(x_tgt.device):
             L.check(self.lib.nb_accel(L.ptr(packed), int(n_src), L.ptr(x_tgt), n, dim, code, L.MODE_CODES[mode], float(G),
-                                      float(eps_sq), L.ptr(table), int(levels or 0), L.ptr(acc), L.ptr(scalars), L.ptr(ws),
+                                      float(eps_sq), L.ptr(table), int(levels or 0), int(bool(uniform[0])), float(uniform[1]),
+                                      L.ptr(acc), L.ptr(scalars), L.ptr(ws),
                                       ws.numel(), L.stream_ptr(x_tgt.device)), "nb_accel")
         return acc
 

@@ -142,11 +142,24 @@ class ShardedGalaxySimulation:
             ops.max_dist_sq(packed, n_src, x, self.softening_sq, self.scalars)
             self._all_reduce(self.scalars[L.SLOT_MAX_D2:L.SLOT_MAX_D2 + 1], dist.ReduceOp.MAX)
             table = ops.build_level_table(self.scalars, x.dtype, self.softening_sq, 0.01, self.G, levels)
-        acc = ops.accel(packed, n_src, x, mode.value, self.G, self.softening_sq, table, levels, self.scalars)
+        acc = ops.accel(packed, n_src, x, mode.value, self.G, self.softening_sq, table, levels, self.scalars,
+                        uniform=self._uniform_mass())
         if mode in _INT_FORCE_SNAP:
             self._all_reduce(self.scalars[L.SLOT_ACC_MIN:L.SLOT_ACC_MIN + 1], dist.ReduceOp.MIN)
             self._all_reduce(self.scalars[L.SLOT_ACC_MAX:L.SLOT_ACC_MAX + 1], dist.ReduceOp.MAX)
         return acc
+
+    def _uniform_mass(self):
+        """(all masses equal on every rank, value): local min/max, all-reduced; cached per masses tensor version."""
+        m = self.masses
+        key = (m.data_ptr(), m._version)
+        if getattr(self, "_uni_key", None) != key:
+            lo, hi = torch.aminmax(m)
+            mm = torch.stack([-lo.double(), hi.double()])
+            self._all_reduce(mm, dist.ReduceOp.MAX)
+            lo, hi = -mm[0].item(), mm[1].item()
+            self._uni_key, self._uni_val = key, (lo == hi, float(lo))
+        return self._uni_val
 
     def _snap_now(self):
         levels = _INT_FORCE_SNAP.get(self.precision_mode, 0)

@@ -134,6 +134,7 @@ class GalaxySimulation:
         ws = buf.bytes("accel_ws", ws_bytes)
         eps_sq = float(self.softening_sq)
         table = None
+        uni, m0 = L.uniform_mass(m) if mode in (PrecisionMode.FLOAT32, PrecisionMode.FLOAT64) else (False, 0.0)
         with torch.cuda.device(x.device):
             st = L.stream_ptr(x.device)
             if levels:
@@ -144,7 +145,8 @@ class GalaxySimulation:
                 L.check(lib.nb_build_level_table(L.ptr(buf.scalars), code, eps_sq, 0.01, float(self.G), levels,
                                                  L.ptr(table), st), "nb_build_level_table")
             L.check(lib.nb_accel(L.ptr(packed), n, L.ptr(x), n, dim, code, mode_code, float(self.G), eps_sq,
-                                 L.ptr(table), levels, L.ptr(acc), L.ptr(buf.scalars), L.ptr(ws), ws.numel(), st),
+                                 L.ptr(table), levels, int(uni), m0, L.ptr(acc), L.ptr(buf.scalars), L.ptr(ws),
+                                 ws.numel(), st),
                     "nb_accel")
         return acc, _INT_FORCE_SNAP.get(mode, 0)
 

@@ -46,7 +46,8 @@ class FakeOps:
         cs = self.chunk_sources(x.dtype)
         chunks = total_chunks or -(-n // cs)
         total = chunks * cs
-        px = x[-1:].expand(total - n, dim)                      # pads: last real position, mass 0
+        far = 1.0e18 if x.dtype == torch.float32 else 1.0e150   # pads: NB_PAD_COORD_*, mass 0
+        px = torch.full((total - n, dim), far, dtype=x.dtype)
         xs = torch.cat([x, px], 0).reshape(chunks, cs, dim)
         ms = torch.cat([m.to(x.dtype), torch.zeros(total - n, dtype=x.dtype)], 0).reshape(chunks, cs)
         if x.dtype == torch.float32:
@@ -128,7 +129,10 @@ class FakeOps:
         return diff, d2, m
 
     def max_dist_sq(self, packed, n_src, x_tgt, eps_sq, scalars):
-        _, d2, _ = self._pairs(packed, n_src, x_tgt, eps_sq)
+        pos, m = self.unpack(packed, n_src, x_tgt.shape[1], x_tgt.dtype)
+        real = pos[:, 0] < 2.5e17                               # padding records are skipped (header spec)
+        diff = pos[real].unsqueeze(0) - x_tgt.unsqueeze(1)
+        d2 = (diff ** 2).sum(dim=-1) + eps_sq
         scalars[L.SLOT_MAX_D2] = max(int(scalars[L.SLOT_MAX_D2]), key(d2.max().item()))
 
     def build_level_table(self, scalars, dtype, eps_sq, min_dist_sq, G, levels):
@@ -136,7 +140,7 @@ class FakeOps:
         t_hi = torch.tensor(unkey(scalars[L.SLOT_MAX_D2]), dtype=dtype).clamp(min=min_dist_sq)
         return {"lo": torch.log(t_lo), "hi": torch.log(t_hi), "levels": levels, "min": min_dist_sq}
 
-    def accel(self, packed, n_src, x_tgt, mode, G, eps_sq, table, levels, scalars):
+    def accel(self, packed, n_src, x_tgt, mode, G, eps_sq, table, levels, scalars, uniform=(False, 0.0)):
         diff, d2, m = self._pairs(packed, n_src, x_tgt, eps_sq)
         if levels:
             u = ora.log_grid_apply(d2, levels, table["min"], table["lo"], table["hi"])

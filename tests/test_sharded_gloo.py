@@ -50,7 +50,7 @@ def test_fake_pack_roundtrip_matches_layout_spec():
             ops.pack(x, m, buf, chunks)
             px, pm = ops.unpack(buf, chunks * cs, dim, dtype)
             assert torch.equal(px[:n], x) and torch.equal(pm[:n], m)
-            assert torch.equal(px[n:], x[-1:].expand(chunks * cs - n, dim)) and (pm[n:] == 0).all()
+            assert (px[n:] > 1e17).all() and (pm[n:] == 0).all()          # pads: far away, zero mass
 
 
 def _worker(rank, world, port, mode, n, dim, ticks, out):
