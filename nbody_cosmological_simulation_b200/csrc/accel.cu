@@ -37,10 +37,11 @@ struct LevelHeader { float lo2, scale, min_val, degenerate; };
 // ======================================================================================================
 // UNI: all source masses are equal (checked by the caller): the per-pair `·m_j` is dropped and the common mass is
 // applied once per target in the finalize pass; padding records then rely on their far-away position (w == 0).
-template <int DIM_, int QMODE, int IPT, int THREADS_, bool UNI = false>
+template <int DIM_, int QMODE, int IPT, int THREADS_, bool UNI = false, int UNROLL = 4>
 struct ForceF32 {
     static constexpr int DIM = DIM_;
     static constexpr int THREADS = THREADS_;
+    static constexpr int TARGETS_PER_THREAD = IPT;
     float2 nx[IPT], ny[IPT], nz[IPT];      // {-x_i, -x_i}: targets, negated and duplicated for packed adds
     float2 ax[IPT], ay[IPT], az[IPT];      // chunk-local sums; .x = even sources, .y = odd sources
     double sx[IPT], sy[IPT], sz[IPT];      // running fp64 sums
@@ -105,7 +106,7 @@ struct ForceF32 {
         const float4* A = reinterpret_cast<const float4*>(s);
         const float4* B4 = reinterpret_cast<const float4*>(s + kChunkABytes);
         const float2* B2 = reinterpret_cast<const float2*>(s + kChunkABytes);
-#pragma unroll 4
+#pragma unroll UNROLL
         for (int p = 0; p < kChunkUnits; ++p) {
             const float4 a = A[p];
             const float2 xs = make_float2(a.x, a.y), ys = make_float2(a.z, a.w);
@@ -186,10 +187,11 @@ __device__ __forceinline__ double inv_dist_cubed(double d2) {     // mass_over_d
     return fma(w, ce, w);
 }
 
-template <int DIM_, int QMODE, int IPT, int THREADS_, bool UNI = false>
+template <int DIM_, int QMODE, int IPT, int THREADS_, bool UNI = false, int UNROLL = 2>
 struct ForceF64 {
     static constexpr int DIM = DIM_;
     static constexpr int THREADS = THREADS_;
+    static constexpr int TARGETS_PER_THREAD = IPT;
     double xi[IPT], yi[IPT], zi[IPT];
     double sx[IPT], sy[IPT], sz[IPT];
     double eps2;
@@ -209,7 +211,7 @@ struct ForceF64 {
         const double2* A = reinterpret_cast<const double2*>(s);
         const double2* B2 = reinterpret_cast<const double2*>(s + kChunkABytes);
         const double* B1 = reinterpret_cast<const double*>(s + kChunkABytes);
-#pragma unroll 2
+#pragma unroll UNROLL
         for (int p = 0; p < kChunkUnits; ++p) {
             const double2 a = A[p];
             double zs = 0.0, m;
@@ -253,6 +255,7 @@ template <int DIM_, int IPT, int THREADS_>
 struct ForceMixed {       // fp32 sources/targets, FLOAT64 mode
     static constexpr int DIM = DIM_;
     static constexpr int THREADS = THREADS_;
+    static constexpr int TARGETS_PER_THREAD = IPT;
     float xi[IPT], yi[IPT], zi[IPT];
     double sx[IPT], sy[IPT], sz[IPT];
     float eps2;
@@ -384,7 +387,7 @@ int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, 
     int ctas_per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, Consumer::THREADS + 32, smem);
     if (e != cudaSuccess) return cuda_status(e);
-    const SplitPlan p = plan_splits(a.n_tgt, a.n_chunks, Consumer::THREADS * kForceIPT, ctas_per_sm, (int)max_by_ws);
+    const SplitPlan p = plan_splits(a.n_tgt, a.n_chunks, Consumer::THREADS * Consumer::TARGETS_PER_THREAD, ctas_per_sm, (int)max_by_ws);
     a.chunks_per_split = p.chunks_per_split;
     kern<<<dim3(p.blocks_i, p.splits), Consumer::THREADS + 32, smem, st>>>(a);
     NB_CUDA_LAUNCH_CHECK();
@@ -396,6 +399,7 @@ int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, 
 
 using namespace nb;
 
+#ifndef NB_TUNE_HARNESS
 extern "C" int64_t nb_accel_workspace_bytes(int64_t n_targets, int dim) {
     if (n_targets <= 0 || (dim != 2 && dim != 3)) return 0;
     // room for the largest j-split the planner may choose for this many targets
@@ -469,3 +473,4 @@ extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_t
     NB_CUDA_LAUNCH_CHECK();
     return NB_OK;
 }
+#endif  // NB_TUNE_HARNESS

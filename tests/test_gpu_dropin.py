@@ -1,0 +1,29 @@
+"""Scripts written against the reference's module names run unchanged through run_script (B200)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_style_driver_runs_unchanged(tmp_path):
+    out = tmp_path / "summary.json"
+    cmd = [sys.executable, "-m", "nbody_cosmological_simulation_b200.run_script",
+           os.path.join(ROOT, "tests", "scripts", "reference_style_driver.py"), "--stars", "600", "--ticks", "200",
+           "--compare", "float64,float32,float16,int8,int4", "--output", str(tmp_path / "plots"), "--json", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "SIMULATION RESULTS SUMMARY" in r.stdout
+    s = json.load(open(out))
+    assert s["float64"]["dtype"] == "torch.float64" and s["float32"]["dtype"] == "torch.float32"
+    for mode in ("float64", "float32", "float16", "int8_sim", "int4_sim"):
+        assert s[mode]["ticks"] == [0, 100, 200] and s[mode]["tick"] == 200
+        e = s[mode]["energy"]
+        drift = abs(e[-1] - e[0]) / abs(e[0])
+        assert drift < (0.05 if mode == "int4_sim" else 1e-3), (mode, drift)
+    # a user-overridden _compute_accelerations (PyTorch on CUDA tensors) goes through the same integrator kernels
+    assert s["override_vs_custom_rel"] < 1e-5
