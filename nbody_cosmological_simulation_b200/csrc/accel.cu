@@ -382,11 +382,9 @@ int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, 
     int smem = stream_smem_bytes(Consumer::DIM);
     if (USE_LUT) smem += (a.levels + 1) * 16;
     auto kern = accel_kernel<Consumer, USE_LUT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return cuda_status(e);
-    int ctas_per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, Consumer::THREADS + 32, smem);
-    if (e != cudaSuccess) return cuda_status(e);
+    int ctas_per_sm = 1;
+    const int frc = kernel_occupancy((const void*)kern, Consumer::THREADS + 32, smem, &ctas_per_sm);
+    if (frc != NB_OK) return frc;
     const SplitPlan p = plan_splits(a.n_tgt, a.n_chunks, Consumer::THREADS * Consumer::TARGETS_PER_THREAD, ctas_per_sm, (int)max_by_ws);
     a.chunks_per_split = p.chunks_per_split;
     kern<<<dim3(p.blocks_i, p.splits), Consumer::THREADS + 32, smem, st>>>(a);

@@ -248,14 +248,15 @@ static int launch_potential(const void* packed_src, int64_t n_src, const void* p
                             int dtype, double eps_sq, double* out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
     constexpr int TH = 256, IPT = 2;
     const int64_t n_chunks = nb_num_chunks(n_src, dtype);
-    const SplitPlan sp = plan_splits(n_tgt, n_chunks, TH * IPT, 3, 64);
+    auto k = potential_kernel<T, TM, DIM, IPT, TH>;
+    const int smem = stream_smem_bytes(DIM);
+    int occ = 1;
+    const int frc = kernel_occupancy((const void*)k, TH + 32, smem, &occ);
+    if (frc != NB_OK) return frc;
+    const SplitPlan sp = plan_splits(n_tgt, n_chunks, TH * IPT, occ, 64);
     const int blocks_i = sp.blocks_i, cps = sp.chunks_per_split, splits = sp.splits;
     const int64_t ctas = (int64_t)blocks_i * splits;
     if (workspace_bytes < ctas * (int64_t)sizeof(double)) return NB_ERR_WORKSPACE_TOO_SMALL;
-    auto k = potential_kernel<T, TM, DIM, IPT, TH>;
-    const int smem = stream_smem_bytes(DIM);
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return cuda_status(e);
     k<<<dim3(blocks_i, splits), TH + 32, smem, st>>>((const char*)packed_src, n_chunks, (const T*)pos_tgt, (const TM*)mass_tgt, n_tgt,
                                                     cps, eps_sq, (double*)workspace);
     NB_CUDA_LAUNCH_CHECK();

@@ -255,22 +255,18 @@ extern "C" int nb_max_dist_sq(const void* packed_src, int64_t n_src, const void*
     if (dtype != NB_F32) return NB_ERR_UNSUPPORTED;       // int modes on fp64 state: no caller in the reference
     constexpr int TH = 256, IPT = 2;
     const int64_t n_chunks = nb_num_chunks(n_src, dtype);
-    // 3 CTAs/SM is what the register budget of these kernels allows; exact occupancy matters little here
-    const SplitPlan sp = plan_splits(n_tgt, n_chunks, TH * IPT, 3, 64);
-    const int blocks_i = sp.blocks_i, cps = sp.chunks_per_split, splits = sp.splits;
     cudaStream_t st = (cudaStream_t)stream;
     const int smem = stream_smem_bytes(dim);
-    if (dim == 2) {
-        auto k = max_dist_kernel<2, IPT, TH>;
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return cuda_status(e);
-        k<<<dim3(blocks_i, splits), TH + 32, smem, st>>>((const char*)packed_src, n_chunks, (const float*)pos_tgt, n_tgt, cps, (float)eps_sq, scalars);
-    } else {
-        auto k = max_dist_kernel<3, IPT, TH>;
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return cuda_status(e);
-        k<<<dim3(blocks_i, splits), TH + 32, smem, st>>>((const char*)packed_src, n_chunks, (const float*)pos_tgt, n_tgt, cps, (float)eps_sq, scalars);
-    }
+    const void* fn = dim == 2 ? (const void*)max_dist_kernel<2, IPT, TH> : (const void*)max_dist_kernel<3, IPT, TH>;
+    int occ = 1;
+    const int frc = kernel_occupancy(fn, TH + 32, smem, &occ);
+    if (frc != NB_OK) return frc;
+    const SplitPlan sp = plan_splits(n_tgt, n_chunks, TH * IPT, occ, 64);
+    const int blocks_i = sp.blocks_i, cps = sp.chunks_per_split, splits = sp.splits;
+    if (dim == 2)
+        max_dist_kernel<2, IPT, TH><<<dim3(blocks_i, splits), TH + 32, smem, st>>>((const char*)packed_src, n_chunks, (const float*)pos_tgt, n_tgt, cps, (float)eps_sq, scalars);
+    else
+        max_dist_kernel<3, IPT, TH><<<dim3(blocks_i, splits), TH + 32, smem, st>>>((const char*)packed_src, n_chunks, (const float*)pos_tgt, n_tgt, cps, (float)eps_sq, scalars);
     NB_CUDA_LAUNCH_CHECK();
     return NB_OK;
 }

@@ -1,0 +1,73 @@
+// Native tick loop: GalaxySimulation.run (simulation.py:145-158) for the stock force, as ONE call.
+// The reference dispatches ~23-55 ATen kernels per tick from Python; here a tick is 3 launches
+// (fused kick-kick-drift + packed emit, force, finalize; int modes add reset / max-d² / level table) issued
+// from C, and for long runs of small systems the tick body is captured once into a CUDA graph and replayed,
+// so the per-tick host cost is one cudaGraphLaunch.
+#include "common.cuh"
+
+using namespace nb;
+
+namespace {
+
+struct TickArgs {
+    void *x, *v, *acc; const void* mass; int64_t n; int dim, dtype, mass_dtype, mode, levels, snap_levels;
+    double G, eps_sq, min_dist_sq, dt; int uniform; double mass_value;
+    void *packed, *table; int64_t* scalars; void* ws; int64_t ws_bytes;
+};
+
+// one tick body: [closing kick of the previous tick +] opening kick + drift (+ packed emit), then the force
+int enqueue_tick(const TickArgs& a, bool first, cudaStream_t st) {
+    const int phase = first ? NB_KDK_KICK_DRIFT : NB_KDK_KICK_KICK_DRIFT;
+    int rc = nb_kdk(a.x, a.v, a.acc, a.x, a.v, a.n, a.dim, a.dtype, a.dt, phase, first ? 0 : a.snap_levels, a.scalars, a.mass,
+                    a.mass_dtype, a.packed, 0, st);
+    if (rc) return rc;
+    if (a.levels > 0) {
+        if ((rc = nb_reset_scalars(a.scalars, st))) return rc;
+        if ((rc = nb_max_dist_sq(a.packed, a.n, a.x, a.n, a.dim, a.dtype, a.eps_sq, a.scalars, st))) return rc;
+        if ((rc = nb_build_level_table(a.scalars, a.dtype, a.eps_sq, a.min_dist_sq, a.G, a.levels, a.table, st))) return rc;
+    }
+    return nb_accel(a.packed, a.n, a.x, a.n, a.dim, a.dtype, a.mode, a.G, a.eps_sq, a.table, a.levels, a.uniform, a.mass_value,
+                    a.acc, a.scalars, a.ws, a.ws_bytes, st);
+}
+
+}  // namespace
+
+extern "C" int nb_run_ticks(void* x, void* v, void* acc, const void* mass, int64_t n, int dim, int dtype, int mass_dtype, int mode,
+                            int levels, int snap_levels, double G, double eps_sq, double min_dist_sq, double dt, int64_t ticks,
+                            int uniform_mass, double mass_value, void* packed, void* level_table, int64_t* scalars,
+                            void* workspace, int64_t workspace_bytes, int use_graph, void* stream) {
+    if (!x || !v || !acc || !mass || !packed || !scalars || !workspace || n <= 0 || ticks < 0) return NB_ERR_INVALID_ARGUMENT;
+    if (ticks == 0) return NB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    TickArgs a{x, v, acc, mass, n, dim, dtype, mass_dtype, mode, levels, snap_levels, G, eps_sq, min_dist_sq, dt,
+               uniform_mass, mass_value, packed, level_table, scalars, workspace, workspace_bytes};
+    int rc = enqueue_tick(a, /*first=*/true, st);
+    if (rc) return rc;
+    int64_t remaining = ticks - 1;
+    if (use_graph && remaining >= 4) {
+        // capture one steady-state tick on a private stream (the caller's may be the legacy default stream, which
+        // cannot be captured), then replay it on the caller's stream
+        cudaStream_t cap = nullptr;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            rc = enqueue_tick(a, /*first=*/false, cap);
+            e = cudaStreamEndCapture(cap, &graph);
+            if (rc == NB_OK && e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+        }
+        if (rc == NB_OK && e == cudaSuccess) {
+            for (; remaining > 0 && e == cudaSuccess; --remaining) e = cudaGraphLaunch(exec, st);
+        }
+        if (exec) cudaGraphExecDestroy(exec);          // deferred until the in-flight launches finish
+        if (graph) cudaGraphDestroy(graph);
+        if (cap) cudaStreamDestroy(cap);
+        if (rc) return rc;
+        if (e != cudaSuccess) { cudaGetLastError(); return cuda_status(e); }
+    }
+    for (; remaining > 0; --remaining)
+        if ((rc = enqueue_tick(a, /*first=*/false, st))) return rc;
+    // closing half kick (with the force snap of INT8/INT4) so that the state is observable
+    return nb_kdk(nullptr, v, acc, nullptr, v, n, dim, dtype, dt, NB_KDK_KICK, snap_levels, scalars, mass, mass_dtype, nullptr, 0, st);
+}

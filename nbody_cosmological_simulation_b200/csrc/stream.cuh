@@ -7,6 +7,7 @@
 // kStages-1 stages, so there is no CTA-wide barrier in the steady state.
 #pragma once
 #include <math.h>
+#include <mutex>
 #include "common.cuh"
 
 namespace nb {
@@ -61,6 +62,35 @@ inline int max_splits_for(int64_t n_tgt, int dim) {
     if (s > 32) s = 32;
     if (s < 1) s = 1;
     return (int)s;
+}
+
+// ---- per-kernel launch facts (host) -----------------------------------------------------------------
+// Dynamic-smem opt-in and resident CTAs/SM are immutable properties of a kernel image on a device; they are
+// looked up once per (kernel, device, smem) and then served from a small table, because the tick loop launches
+// the same kernels thousands of times (and may be under stream capture, where attribute calls are best avoided).
+struct KernelFacts { const void* fn; int dev; int smem; int threads; int occ; };
+
+inline int kernel_occupancy(const void* fn, int threads, int smem, int* occ_out) {
+    static std::mutex mu;
+    static KernelFacts table[64];
+    static int used = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < used; ++i)
+        if (table[i].fn == fn && table[i].dev == dev && table[i].smem == smem && table[i].threads == threads) {
+            *occ_out = table[i].occ;
+            return NB_OK;
+        }
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    if (occ < 1) occ = 1;
+    if (used < 64) table[used++] = KernelFacts{fn, dev, smem, threads, occ};
+    *occ_out = occ;
+    return NB_OK;
 }
 
 // Consumer concept:

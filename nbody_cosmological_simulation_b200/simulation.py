@@ -215,24 +215,39 @@ class GalaxySimulation:
             self.velocities = v
         self.tick += 1
 
+    # below this many particles a tick is launch-latency bound: replay it from a CUDA graph
+    GRAPH_MAX_STARS = 65536
+
     def _run_fused(self, ticks: int):
-        """`ticks` stock ticks with the closing half kick of tick t fused into the opening of tick t+1."""
+        """`ticks` stock ticks in ONE native call (nb_run_ticks): the closing half kick of tick t is fused into the
+        opening of tick t+1, the tick body is replayed from a CUDA graph for small systems, and the state is
+        updated in place on private copies (tensors the caller still holds are never mutated)."""
+        if ticks <= 0:
+            return
+        lib, buf = L.load(), self._buf()
         x, v, m, a = self._promoted_state(self.accelerations)
-        snap_levels = 0
-        pending = False                       # True: `a` still has to be applied as the closing half kick
-        for _ in range(ticks):
-            phase = L.KDK_KICK_KICK_DRIFT if pending else L.KDK_KICK_DRIFT
-            x, v = self._kdk(phase, x, v, a, m, snap_levels=snap_levels if pending else 0, emit_packed=True)
-            packed = self._buf().bytes(f"packed{L.dtype_code(x)}", 0)
-            a, snap_levels = self._accelerations_raw(x, m, packed)
-            if a.dtype != x.dtype:            # mode switched to FLOAT64 mid-run on fp32 state: promote once
-                x, v = x.to(a.dtype), v.to(a.dtype)
-                self._packed_key = None
-            pending = True
-            self.tick += 1
-        if pending:
-            _, v = self._kdk(L.KDK_KICK, None, v, a, m, snap_levels=snap_levels)
+        mode = self.precision_mode
+        # private buffers: .clone() unless promotion already made a fresh copy
+        x = x.clone() if x is self.positions or x.data_ptr() == self.positions.data_ptr() else x
+        v = v.clone() if v is self.velocities or v.data_ptr() == self.velocities.data_ptr() else v
+        a = a.clone() if a.data_ptr() == self.accelerations.data_ptr() else a
+        n, dim = x.shape
+        code = L.dtype_code(x)
+        levels = levels_for_mode(mode) or 0
+        snap_levels = _INT_FORCE_SNAP.get(mode, 0)
+        uni, m0 = L.uniform_mass(m) if mode in (PrecisionMode.FLOAT32, PrecisionMode.FLOAT64) else (False, 0.0)
+        packed = buf.bytes(f"packed{code}", lib.nb_packed_bytes(n, dim, code))
+        table = buf.bytes("level_table", lib.nb_level_table_bytes(levels)) if levels else None
+        ws = buf.bytes("accel_ws", lib.nb_accel_workspace_bytes(n, dim))
+        with torch.cuda.device(x.device):
+            L.check(lib.nb_run_ticks(L.ptr(x), L.ptr(v), L.ptr(a), L.ptr(m), n, dim, code, L.dtype_code(m),
+                                     L.MODE_CODES[mode.value], levels, snap_levels, float(self.G), float(self.softening_sq),
+                                     0.01, float(self.dt), int(ticks), int(uni), m0, L.ptr(packed), L.ptr(table),
+                                     L.ptr(buf.scalars), L.ptr(ws), ws.numel(), int(n <= self.GRAPH_MAX_STARS),
+                                     L.stream_ptr(x.device)), "nb_run_ticks")
+        self._packed_key = self._packed_cache_key(x, m, packed)      # packed holds the records of the final positions
         self.positions, self.velocities, self.accelerations = x, v, a
+        self.tick += int(ticks)
 
     def run(self, num_ticks: int, callback: Callable = None, callback_interval: int = 100):
         """Run `num_ticks` ticks; `callback(sim, sim.tick)` every `callback_interval` (simulation.py:145-158)."""

@@ -122,10 +122,10 @@ def _slab_diff_d2(pos: torch.Tensor, i0: int, i1: int, eps_sq: float):
     return diff, (diff ** 2).sum(dim=-1) + eps_sq
 
 
-def _eye_rows(i0: int, i1: int, n: int) -> torch.Tensor:
+def _eye_rows(i0: int, i1: int, n: int, device=None) -> torch.Tensor:
     """Rows i0:i1 of the fp32 N×N identity without materialising all of it."""
-    e = torch.zeros(i1 - i0, n)
-    idx = torch.arange(i0, i1)
+    e = torch.zeros(i1 - i0, n, device=device)
+    idx = torch.arange(i0, i1, device=device)
     e[idx - i0, idx] = 1.0
     return e
 
@@ -165,7 +165,7 @@ def accelerations_presnap(pos: torch.Tensor, mass: torch.Tensor, mode: str, G: f
             u = log_grid_apply(d2, lv, 0.01, *bounds)
         ff = G / (u ** 1.5)                                 # :97,101  (reciprocal * G)
         ff = ff * mass.unsqueeze(0)                         # :105
-        not_self = 1 - _eye_rows(i0, i1, n)                 # :108 (fp32 eye)
+        not_self = 1 - _eye_rows(i0, i1, n, pos.device)               # :108 (fp32 eye)
         ff = ff * not_self
         parts.append((ff.unsqueeze(-1) * diff).sum(dim=1))  # :112
     return parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
@@ -243,7 +243,7 @@ def potential_energy(pos: torch.Tensor, mass: torch.Tensor, G: float = 0.001, so
         _, d2 = _slab_diff_d2(pos, i0, i1, eps_sq)
         dist = torch.sqrt(d2)                               # :183
         mprod = mass.unsqueeze(0) * mass[i0:i1].unsqueeze(1)  # :186
-        upper = torch.triu(torch.ones(i1 - i0, n, dtype=dist.dtype), diagonal=1 + i0)  # :189
+        upper = torch.triu(torch.ones(i1 - i0, n, dtype=dist.dtype, device=dist.device), diagonal=1 + i0)  # :189
         s = (mprod * upper / dist).sum()                    # :190
         total = s if total is None else total + s
     return (-G * total).item()
@@ -259,7 +259,7 @@ def rotation_curve(pos: torch.Tensor, vel: torch.Tensor, num_bins: int = 20,
     if max_radius is None:
         max_radius = r.max().item()                         # :51
     vt = torch.abs(pos[:, 0] * vel[:, 1] - pos[:, 1] * vel[:, 0]) / r.clamp(min=0.1)  # :55-57
-    edges = torch.linspace(0, max_radius, num_bins + 1)     # :60
+    edges = torch.linspace(0, max_radius, num_bins + 1, device=pos.device)     # :60
     centres = (edges[:-1] + edges[1:]) / 2                  # :61
     means, counts = [], []
     for b in range(num_bins):
@@ -267,7 +267,7 @@ def rotation_curve(pos: torch.Tensor, vel: torch.Tensor, num_bins: int = 20,
         c = int(inside.sum().item())
         counts.append(c)
         means.append(vt[inside].mean().item() if c > 0 else float("nan"))  # :66-69
-    return {"radii": centres.numpy(), "velocities": np.array(means), "num_stars_per_bin": counts}
+    return {"radii": centres.cpu().numpy(), "velocities": np.array(means), "num_stars_per_bin": counts}
 
 
 def galaxy_radius(pos: torch.Tensor, percentile: float = 90) -> float:
