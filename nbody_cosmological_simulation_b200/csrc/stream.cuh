@@ -72,23 +72,30 @@ struct KernelFacts { const void* fn; int dev; int smem; int threads; int occ; };
 
 inline int kernel_occupancy(const void* fn, int threads, int smem, int* occ_out) {
     static std::mutex mu;
-    static KernelFacts table[64];
+    static KernelFacts table[96];
     static int used = 0;
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(mu);
-    for (int i = 0; i < used; ++i)
-        if (table[i].fn == fn && table[i].dev == dev && table[i].smem == smem && table[i].threads == threads) {
+    int opted_in = -1;                                  // largest dynamic-smem size already enabled for this kernel
+    for (int i = 0; i < used; ++i) {
+        if (table[i].fn != fn || table[i].dev != dev) continue;
+        if (table[i].smem > opted_in) opted_in = table[i].smem;
+        if (table[i].smem == smem && table[i].threads == threads) {
             *occ_out = table[i].occ;
             return NB_OK;
         }
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return cuda_status(e);
+    }
+    if (smem > opted_in) {                              // only ever raise the opt-in (level tables vary in size)
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_status(e);
+    }
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem);
     if (e != cudaSuccess) return cuda_status(e);
     if (occ < 1) occ = 1;
-    if (used < 64) table[used++] = KernelFacts{fn, dev, smem, threads, occ};
+    if (used < 96) table[used++] = KernelFacts{fn, dev, smem, threads, occ};
+    else if (smem > opted_in) table[95] = KernelFacts{fn, dev, smem, threads, occ};
     *occ_out = occ;
     return NB_OK;
 }
