@@ -1,0 +1,68 @@
+"""Multi-GPU correctness check (run under torchrun with NCCL): the sharded engine against the single-GPU engine
+on rank 0, same inputs.  Prints one line per case and exits non-zero on mismatch.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/run_sharded_check.py
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import nbody_cosmological_simulation_b200 as nb  # noqa: E402
+from nbody_cosmological_simulation_b200.sharded import ShardedGalaxySimulation  # noqa: E402
+from oracle import reference_port as ora  # noqa: E402  (synthetic inputs only)
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    cases = [(5000, 2, "float32", torch.float32), (5000, 2, "int4_sim", torch.float32), (5000, 2, "int8_sim", torch.float32),
+             (4099, 3, "float64", torch.float64), (6000, 3, "float64", torch.float32), (7001, 3, "float16", torch.float32),
+             (65536, 3, "float32", torch.float32)]
+    for n, dim, mode, dtype in cases:
+        if dim == 2:
+            torch.manual_seed(11)
+            pos, vel, mass = nb.create_disk_galaxy(n, device=torch.device("cpu"))
+        else:
+            pos, vel, mass = ora.uniform_box(n, seed=5, dim=3)
+            mass = mass * (1 + (torch.arange(n) % 4 == 0).to(mass.dtype))          # non-uniform masses
+        pos, vel, mass = pos.to(dtype).to(dev), vel.to(dtype).to(dev), mass.to(dtype).to(dev)
+        pm = nb.get_mode_from_string(mode)
+        sh = ShardedGalaxySimulation(pos, vel, mass, precision_mode=pm)
+        e0 = sh.get_total_energy()
+        sh.run(5)
+        st = sh.get_state()
+        acc = sh.gather(sh.accelerations)
+        e1 = sh.get_total_energy()
+        if rank == 0:
+            one = nb.GalaxySimulation(pos, vel, mass, precision_mode=pm)
+            f0 = one.get_total_energy()
+            one.run(5)
+            f1 = one.get_total_energy()
+            tol = 1e-12 if one.positions.dtype == torch.float64 else 1e-6
+            dx = (st["positions"] - one.positions).abs().max().item()
+            dv = (st["velocities"] - one.velocities).abs().max().item()
+            if mode in ("int4_sim", "int8_sim"):
+                da = ((acc - one.accelerations).abs() > 1e-6 * one.accelerations.abs().max()).float().mean().item()
+                good = da <= 0.01
+            else:
+                da = ((acc - one.accelerations).norm(dim=1) / one.accelerations.norm(dim=1)).max().item()
+                good = da <= tol * 10 and dx <= tol * 20 and dv <= tol * 20
+            good = good and abs(e0 - f0) <= 1e-6 * abs(f0) and abs(e1 - f1) <= (1e-3 if "int" in mode else 1e-6) * abs(f1)
+            good = good and st["positions"].dtype == one.positions.dtype and sh.tick == one.tick
+            print(f"world={world} N={n} D={dim} {mode:9s} {str(dtype):14s} dpos={dx:.2e} dvel={dv:.2e} dacc={da:.2e} "
+                  f"E0 {e0:.8g}/{f0:.8g} E1 {e1:.8g}/{f1:.8g} counts={sh.plan.count[:3]}... {'OK' if good else 'MISMATCH'}", flush=True)
+            ok = ok and good
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
