@@ -145,6 +145,7 @@ def measured_fp32_peak():
     try:
         out = subprocess.run([exe], capture_output=True, text=True, timeout=120, check=True).stdout
         r = json.loads(out)["results"]
+        measured_fp32_peak.all = r
         return r["ffma"]["Tflops"], "tools/peaks FFMA microbenchmark, measured live in this run"
     except Exception:
         try:
@@ -281,8 +282,60 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = interactions_per_step * K / te.item()
 
+    # -------- secondary measurements (N=1 only): fp64 force rate and the HBM-bound fused integrator --------
+    extra = {}
+    if world == 1:
+        hbm_peak = None
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_peak = json.load(f).get("hbm_gbs")
+        except Exception:
+            pass
+        # fused kick-kick-drift + packed emit: one HBM round trip of the state, L2 flushed before each launch
+        x, v, m = sim._state()
+        a = sim.accelerations
+        ev = []
+        for i in range(12):
+            flush_buf.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sim._kdk(L.KDK_KICK_KICK_DRIFT, x, v, a, m, emit_packed=True)
+            e1.record()
+            ev.append((e0, e1))
+        torch.cuda.synchronize()
+        kdk_ms = sorted(p.elapsed_time(q) for p, q in ev[2:])
+        kdk_ms = kdk_ms[len(kdk_ms) // 2]
+        sim._packed_key = None
+        kdk_bytes = N_PARTICLES * (3 * DIM * 4 + 2 * DIM * 4 + 4 + 16)     # read x,v,a + mass, write x,v + packed record
+        extra["kdk"] = {"kernel": "kdk_kernel<float,3,float,KICK_KICK_DRIFT>", "bound": "hbm", "bytes_per_launch": kdk_bytes,
+                        "ms": kdk_ms, "achieved": kdk_bytes / (kdk_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": (kdk_bytes / (kdk_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if hbm_peak else "unavailable",
+                        "note": "84 MB per launch: a 28 us kernel, latency- rather than bandwidth-limited at this N"}
+        # float64 state / FLOAT64 mode at the same N (the metric is quoted for fp64 and fp32)
+        sim64 = nb.GalaxySimulation(pos.double().to(dev), vel.double().to(dev), mass.double().to(dev),
+                                    precision_mode=nb.PrecisionMode.FLOAT64, G=G, softening=SOFTENING, dt=DT, device=dev)
+        x64, _, m64 = sim64._state()
+        pk = sim64._pack(x64, m64)
+        sim64._accelerations_raw(x64, m64, pk)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            sim64._accelerations_raw(x64, m64, pk)
+        e1.record()
+        torch.cuda.synchronize()
+        f64_ms = e0.elapsed_time(e1) / 2
+        extra["fp64"] = {"kernel": "accel_kernel<ForceF64<3,Q_F64,...>>", "ms_per_force_pass": f64_ms,
+                         "value": interactions_per_step / (f64_ms * 1e-3), "unit": UNIT,
+                         "tflops_at_20_flop": FLOP_PER_INTERACTION * interactions_per_step / (f64_ms * 1e-3) / 1e12}
+        del sim64
+
     if rank == 0:
         peak_tf, peak_src = measured_fp32_peak()
+        allp = getattr(measured_fp32_peak, "all", None)
+        if "fp64" in extra and allp:
+            extra["fp64"]["peak_dfma_tflops"] = allp["dfma"]["Tflops"]
+            extra["fp64"]["frac"] = extra["fp64"]["tflops_at_20_flop"] / allp["dfma"]["Tflops"]
         f_ms = sum(force_ms) / len(force_ms)
         inter_per_launch = interactions_per_step / world
         achieved_tf = FLOP_PER_INTERACTION * inter_per_launch / (f_ms * 1e-3) / 1e12
@@ -309,7 +362,8 @@ def main():
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_dict(world),
                 "tflops_at_20_flop": value * FLOP_PER_INTERACTION / 1e12,
-                "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                "roofline": roofline, "roofline_kdk": extra.get("kdk"), "fp64": extra.get("fp64"),
+                "cpu_baseline": cpu, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "note": "state uploaded from pinned host memory and downloaded again every step through "
                                 "GalaxySimulation (N=1) / ShardedGalaxySimulation attributes + run(1)"},

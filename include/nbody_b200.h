@@ -100,12 +100,15 @@ int nb_pack_sources(const void* pos, const void* mass, int64_t n, int dim, int d
 /* Bytes of scratch nb_accel needs for n_targets targets (partial sums of the j-split). */
 int64_t nb_accel_workspace_bytes(int64_t n_targets, int dim);
 
-/* INT8_SIM / INT4_SIM / CUSTOM pass 1 (quantization.py:112-113): max over all target×source
- * pairs of d² (exact reference rounding sequence, state dtype) -> scalars[NB_SLOT_MAX_D2] (atomic
- * max; reset it with nb_reset_scalars first).  After a cross-rank MAX all-reduce of that slot the
- * LUT is built by nb_build_level_table. */
-int nb_max_dist_sq(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt,
-                   int dim, int dtype, double eps_sq, int64_t* scalars, void* stream);
+/* INT8_SIM / INT4_SIM / CUSTOM pass 1 (quantization.py:112-113): max over ALL pairs of the n_src packed
+ * sources of d² (the reference's exact rounding sequence, state dtype) -> scalars[NB_SLOT_MAX_D2] (atomic max;
+ * reset it with nb_reset_scalars first).  Exact, but O(n) + O(C²): only sources in the outer shell of the point
+ * set (R_i >= D_lb − R_max about the bounding-box centre) can form the farthest pair, and only those C candidates
+ * are compared pairwise.  In a sharded run every rank holds the full source set and gets the global value; the
+ * cross-rank MAX all-reduce of the slot is then a no-op kept for symmetry. */
+int64_t nb_max_dist_workspace_bytes(int64_t n_src);
+int nb_max_dist_sq(const void* packed_src, int64_t n_src, int dim, int dtype, double eps_sq, int64_t* scalars,
+                   void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Bytes of the level table for `levels` grid levels. */
 int64_t nb_level_table_bytes(int levels);
@@ -159,7 +162,7 @@ int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_o
  * to issuing those calls one by one.  levels = d² grid levels (0 for float modes), snap_levels = force grid levels
  * (INT8/INT4, else 0).  use_graph != 0 captures the tick body once into a CUDA graph and replays it (worth it for
  * small systems where launch latency dominates).  packed: nb_packed_bytes; level_table: nb_level_table_bytes (or
- * NULL); workspace: nb_accel_workspace_bytes. */
+ * NULL); workspace: max(nb_accel_workspace_bytes, nb_max_dist_workspace_bytes) — the two uses never overlap. */
 int nb_run_ticks(void* x, void* v, void* acc, const void* mass, int64_t n, int dim, int dtype, int mass_dtype,
                  int mode, int levels, int snap_levels, double G, double eps_sq, double min_dist_sq, double dt,
                  int64_t ticks, int uniform_mass, double mass_value, void* packed, void* level_table,

@@ -26,6 +26,7 @@ struct AccelArgs {
     double eps_sq;
     const void* table;        // level table (Q_LUT)
     int levels;
+    float neg_zero;           // -0.0f, passed at run time so that the compiler cannot fold fma(d, d, -0) back into a mul
 };
 
 // Level table layout (Q_LUT): float4 entry[k] = { T_{k+1}, g_k, g_{k+1}, 0 } for k = 0..L-1, preceded by a
@@ -46,6 +47,7 @@ struct ForceF32 {
     float2 ax[IPT], ay[IPT], az[IPT];      // chunk-local sums; .x = even sources, .y = odd sources
     double sx[IPT], sy[IPT], sz[IPT];      // running fp64 sums
     float2 eps2;
+    float neg_zero;
     const float4* lut;                     // shared-memory copy of the level table (Q_LUT)
     float lo2, scale, min_val;
 
@@ -62,10 +64,12 @@ struct ForceF32 {
         }
         const float e = (float)a.eps_sq;                // softening_sq cast to the tensor dtype (simulation.py:86)
         eps2 = make_float2(e, e);
+        neg_zero = a.neg_zero;
         lut = lut_smem;
         if (QMODE == Q_LUT) {
             const float4 h = lut_smem[0];
-            lo2 = h.x; scale = h.y; min_val = h.z;
+            scale = h.y; min_val = h.z;
+            lo2 = fmaf(-h.x, h.y, -0.5f + 1.0f / 64.0f);     // additive constant of the level estimate (see lut_factor)
         }
     }
 
@@ -78,28 +82,30 @@ struct ForceF32 {
             if (DIM == 3) d2 = fma2(dz, dz, d2);
             return d2;
         } else {
-            // scalar _rn ops on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (seen in SASS),
-            // which would change d² by an ulp and flip fp16/bf16/grid snaps; scalar FMUL/FADD are left alone.
-            float sx = __fadd_rn(__fmul_rn(dx.x, dx.x), __fmul_rn(dy.x, dy.x));   // rn(rn(dx²)+rn(dy²))   simulation.py:86
-            float sy = __fadd_rn(__fmul_rn(dx.y, dx.y), __fmul_rn(dy.y, dy.y));
-            if (DIM == 3) {
-                sx = __fadd_rn(sx, __fmul_rn(dz.x, dz.x));                           // rn(· + rn(dz²))
-                sy = __fadd_rn(sy, __fmul_rn(dz.y, dz.y));
-            }
-            return make_float2(__fadd_rn(sx, eps2.x), __fadd_rn(sy, eps2.y));        // rn(· + ε²)
+            // The reference's exact rounding sequence rn(rn(rn(dx²)+rn(dy²))[+rn(dz²)])+ε²) with packed ops.  ptxas
+            // contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (seen in SASS; changes d² by an ulp and flips fp16/bf16/
+            // grid snaps), so each square is written as fma(d, d, −0) — exactly rn(d²) — with the −0 a run-time kernel
+            // argument: a literal −0 is folded back into a mul and contracted again (also seen in SASS).
+            const float2 nz2 = make_float2(neg_zero, neg_zero);
+            float2 s = add2(fma2(dx, dx, nz2), fma2(dy, dy, nz2));
+            if (DIM == 3) s = add2(s, fma2(dz, dz, nz2));
+            return add2(s, eps2);
         }
     }
 
     __device__ __forceinline__ float lut_factor(float d2) const {
-        // t = clamp(d², min); k = round((log t − lo)/(hi − lo)·(L−1)) found exactly from a MUFU.LG2
-        // estimate biased to k−1 ≤ k_lo ≤ k plus one comparison against the exact threshold T_{k_lo+1}.
+        // t = clamp(d², min); k = round((log t − lo)/(hi − lo)·(L−1)) found exactly from a MUFU.LG2 estimate biased to
+        // k−1 ≤ k_lo ≤ k plus one comparison against the exact threshold T_{k_lo+1}.  t ≥ t_lo by construction, so only
+        // the upper clamp is needed (padding records / Inf / NaN); rint() is done with the 1.5·2²³ magic add (FMA
+        // pipe + LOP3) instead of F2I, which would share the 16-lane XU pipe with MUFU.LG2.
         const float t = fmaxf(d2, min_val);
-        float kf = fmaf(lg2_approx(t) - lo2, scale, -0.5f + 1.0f / 64.0f);   // (n_est − ½ + margin): rint() below gives floor-ish
-        kf = fminf(fmaxf(kf, 0.f), (float)(levels_m1));
-        const int k_lo = __float2int_rn(kf);
+        float kf = fmaf(lg2_approx(t), scale, lo2);                      // lo2 holds (−lo2·scale − ½ + margin), see init()
+        kf = fminf(kf, levels_m1_f);
+        const int k_lo = __float_as_int(kf + 12582912.0f) & 0x3fffff;
         const float4 e = lut[1 + k_lo];
         return t >= e.x ? e.z : e.y;
     }
+    float levels_m1_f;
     int levels_m1;
 
     __device__ __forceinline__ void chunk(const unsigned char* s, int64_t) {
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(Consumer::THREADS + 32) accel_kernel(const Acc
     }
     Consumer cons;
     if (is_consumer) cons.init(a, lut_smem);
-    if constexpr (USE_LUT) cons.levels_m1 = a.levels - 1;
+    if constexpr (USE_LUT) cons.levels_m1_f = (float)(a.levels - 1);
     const int64_t c0 = (int64_t)blockIdx.y * a.chunks_per_split;
     const int64_t c1 = min(a.n_chunks, c0 + (int64_t)a.chunks_per_split);
     stream_sources(a.src, c0, c1, cons);
@@ -431,6 +437,7 @@ extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_t
     a.eps_sq = eps_sq;
     a.table = level_table;
     a.levels = levels;
+    a.neg_zero = -0.0f;
 
     int splits = 0, rc = NB_ERR_INVALID_ARGUMENT;
     constexpr int TH = kForceThreads, IPT = kForceIPT;

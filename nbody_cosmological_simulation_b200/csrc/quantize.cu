@@ -38,72 +38,6 @@ __device__ __forceinline__ T log_grid_value(T k, T lo, T span, T lm1, T min_val)
     return q_max(q_exp(q_add(q_mul(q_div(k, lm1), span), lo)), min_val);
 }
 
-// ---- pass 1: max d² over all pairs (fp32 state) ----------------------------------------------------
-template <int DIM_, int IPT, int THREADS_>
-struct MaxDistF32 {
-    static constexpr int DIM = DIM_;
-    static constexpr int THREADS = THREADS_;
-    float2 nx[IPT], ny[IPT], nz[IPT];
-    float best;                              // max over pairs of rn(rn(dx²)+rn(dy²)[+rn(dz²)]); ε² added once at the end
-    __device__ __forceinline__ void init(const float* pos, int64_t n_tgt) {
-#pragma unroll
-        for (int t = 0; t < IPT; ++t) {
-            int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
-            if (i >= n_tgt) i = n_tgt - 1;
-            const float x = pos[i * DIM + 0], y = pos[i * DIM + 1], z = DIM == 3 ? pos[i * DIM + 2] : 0.f;
-            nx[t] = make_float2(-x, -x); ny[t] = make_float2(-y, -y); nz[t] = make_float2(-z, -z);
-        }
-        best = 0.f;
-    }
-    __device__ __forceinline__ void chunk(const unsigned char* s, int64_t) {
-        const float4* A = reinterpret_cast<const float4*>(s);
-        const float4* B4 = reinterpret_cast<const float4*>(s + kChunkABytes);
-#pragma unroll 4
-        for (int p = 0; p < kChunkUnits; ++p) {
-            const float4 a = A[p];
-            // padding records sit at kPadCoordF32: turn them into NaN so that fmaxf() below ignores their pairs
-            const float nan = __int_as_float(0x7fffffff);
-            const float2 xs = make_float2(a.x > kPadDetectF32 ? nan : a.x, a.y > kPadDetectF32 ? nan : a.y);
-            const float2 ys = make_float2(a.z, a.w);
-            float2 zs = make_float2(0.f, 0.f);
-            if (DIM == 3) { const float4 b = B4[p]; zs = make_float2(b.x, b.y); }
-#pragma unroll
-            for (int t = 0; t < IPT; ++t) {
-                const float2 dx = add2(xs, nx[t]), dy = add2(ys, ny[t]);
-                // scalar _rn ops: ptxas would contract the packed mul.rn/add.rn pair into FFMA2 (see accel.cu)
-                float qx = __fadd_rn(__fmul_rn(dx.x, dx.x), __fmul_rn(dy.x, dy.x));
-                float qy = __fadd_rn(__fmul_rn(dx.y, dx.y), __fmul_rn(dy.y, dy.y));
-                if (DIM == 3) {
-                    const float2 dz = add2(zs, nz[t]);
-                    qx = __fadd_rn(qx, __fmul_rn(dz.x, dz.x));
-                    qy = __fadd_rn(qy, __fmul_rn(dz.y, dz.y));
-                }
-                const float2 q = make_float2(qx, qy);
-                best = fmaxf(best, fmaxf(q.x, q.y));
-            }
-        }
-    }
-};
-
-template <int DIM, int IPT, int THREADS>
-__global__ void __launch_bounds__(THREADS + 32) max_dist_kernel(const char* __restrict__ src, int64_t n_chunks,
-                                                                const float* __restrict__ pos_tgt, int64_t n_tgt,
-                                                                int chunks_per_split, float eps2, int64_t* __restrict__ scalars) {
-    __shared__ float red[32];
-    MaxDistF32<DIM, IPT, THREADS> cons;
-    const bool is_consumer = threadIdx.x < THREADS;
-    if (is_consumer) cons.init(pos_tgt, n_tgt); else cons.best = 0.f;
-    const int64_t c0 = (int64_t)blockIdx.y * chunks_per_split;
-    const int64_t c1 = min(n_chunks, c0 + (int64_t)chunks_per_split);
-    stream_sources(src, c0, c1, cons);
-    const float m = block_reduce(cons.best, OpMax(), 0.f, red);
-    if (threadIdx.x == 0) {
-        // rn is monotone: max_pairs rn(s + ε²) == rn(max_pairs s + ε²)
-        const double d2 = (double)__fadd_rn(m, eps2);
-        atomicMax(reinterpret_cast<long long*>(scalars + NB_SLOT_MAX_D2), (long long)key_from_double(d2));
-    }
-}
-
 // ---- level table -------------------------------------------------------------------------------------
 struct LevelHeader { float lo2, scale, min_val, degenerate; };
 
@@ -245,28 +179,6 @@ using namespace nb;
 extern "C" int nb_reset_scalars(int64_t* scalars, void* stream) {
     if (!scalars) return NB_ERR_INVALID_ARGUMENT;
     reset_scalars_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scalars);
-    NB_CUDA_LAUNCH_CHECK();
-    return NB_OK;
-}
-
-extern "C" int nb_max_dist_sq(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt, int dim, int dtype,
-                              double eps_sq, int64_t* scalars, void* stream) {
-    if (!packed_src || !pos_tgt || !scalars || n_src <= 0 || n_tgt <= 0 || (dim != 2 && dim != 3)) return NB_ERR_INVALID_ARGUMENT;
-    if (dtype != NB_F32) return NB_ERR_UNSUPPORTED;       // int modes on fp64 state: no caller in the reference
-    constexpr int TH = 256, IPT = 2;
-    const int64_t n_chunks = nb_num_chunks(n_src, dtype);
-    cudaStream_t st = (cudaStream_t)stream;
-    const int smem = stream_smem_bytes(dim);
-    const void* fn = dim == 2 ? (const void*)max_dist_kernel<2, IPT, TH> : (const void*)max_dist_kernel<3, IPT, TH>;
-    int occ = 1;
-    const int frc = kernel_occupancy(fn, TH + 32, smem, &occ);
-    if (frc != NB_OK) return frc;
-    const SplitPlan sp = plan_splits(n_tgt, n_chunks, TH * IPT, occ, 64);
-    const int blocks_i = sp.blocks_i, cps = sp.chunks_per_split, splits = sp.splits;
-    if (dim == 2)
-        max_dist_kernel<2, IPT, TH><<<dim3(blocks_i, splits), TH + 32, smem, st>>>((const char*)packed_src, n_chunks, (const float*)pos_tgt, n_tgt, cps, (float)eps_sq, scalars);
-    else
-        max_dist_kernel<3, IPT, TH><<<dim3(blocks_i, splits), TH + 32, smem, st>>>((const char*)packed_src, n_chunks, (const float*)pos_tgt, n_tgt, cps, (float)eps_sq, scalars);
     NB_CUDA_LAUNCH_CHECK();
     return NB_OK;
 }

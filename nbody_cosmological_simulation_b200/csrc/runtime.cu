@@ -23,7 +23,8 @@ int enqueue_tick(const TickArgs& a, bool first, cudaStream_t st) {
     if (rc) return rc;
     if (a.levels > 0) {
         if ((rc = nb_reset_scalars(a.scalars, st))) return rc;
-        if ((rc = nb_max_dist_sq(a.packed, a.n, a.x, a.n, a.dim, a.dtype, a.eps_sq, a.scalars, st))) return rc;
+        // the force workspace is idle during pass 1: it doubles as the candidate buffer of the max-d² search
+        if ((rc = nb_max_dist_sq(a.packed, a.n, a.dim, a.dtype, a.eps_sq, a.scalars, a.ws, a.ws_bytes, st))) return rc;
         if ((rc = nb_build_level_table(a.scalars, a.dtype, a.eps_sq, a.min_dist_sq, a.G, a.levels, a.table, st))) return rc;
     }
     return nb_accel(a.packed, a.n, a.x, a.n, a.dim, a.dtype, a.mode, a.G, a.eps_sq, a.table, a.levels, a.uniform, a.mass_value,

@@ -68,9 +68,11 @@ class CudaOps:
     def max_dist_sq(self, packed, n_src, x_tgt, eps_sq, scalars):
         L.require_cuda(packed, x_tgt, scalars)
         n, dim = x_tgt.shape
+        ws = self._scratch("maxdist", self.lib.nb_max_dist_workspace_bytes(int(n_src)), x_tgt.device)
         with torch.cuda.device(x_tgt.device):
-            L.check(self.lib.nb_max_dist_sq(L.ptr(packed), int(n_src), L.ptr(x_tgt), n, dim, L.dtype_code(x_tgt),
-                                            float(eps_sq), L.ptr(scalars), L.stream_ptr(x_tgt.device)), "nb_max_dist_sq")
+            L.check(self.lib.nb_max_dist_sq(L.ptr(packed), int(n_src), dim, L.dtype_code(x_tgt), float(eps_sq),
+                                            L.ptr(scalars), L.ptr(ws), ws.numel(), L.stream_ptr(x_tgt.device)),
+                    "nb_max_dist_sq")
 
     def build_level_table(self, scalars, dtype, eps_sq, min_dist_sq, G, levels):
         L.require_cuda(scalars)

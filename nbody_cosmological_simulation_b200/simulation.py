@@ -130,7 +130,7 @@ class GalaxySimulation:
         levels = levels_for_mode(mode) or 0
         out_dtype = torch.float64 if (code == L.NB_F64 or mode == PrecisionMode.FLOAT64) else torch.float32
         acc = torch.empty((n, dim), dtype=out_dtype, device=x.device)
-        ws_bytes = lib.nb_accel_workspace_bytes(n, dim)
+        ws_bytes = max(lib.nb_accel_workspace_bytes(n, dim), lib.nb_max_dist_workspace_bytes(n) if levels else 0)
         ws = buf.bytes("accel_ws", ws_bytes)
         eps_sq = float(self.softening_sq)
         table = None
@@ -139,8 +139,8 @@ class GalaxySimulation:
             st = L.stream_ptr(x.device)
             if levels:
                 L.check(lib.nb_reset_scalars(L.ptr(buf.scalars), st), "nb_reset_scalars")
-                L.check(lib.nb_max_dist_sq(L.ptr(packed), n, L.ptr(x), n, dim, code, eps_sq, L.ptr(buf.scalars), st),
-                        "nb_max_dist_sq")
+                L.check(lib.nb_max_dist_sq(L.ptr(packed), n, dim, code, eps_sq, L.ptr(buf.scalars), L.ptr(ws), ws.numel(),
+                                           st), "nb_max_dist_sq")
                 table = buf.bytes("level_table", lib.nb_level_table_bytes(levels))
                 L.check(lib.nb_build_level_table(L.ptr(buf.scalars), code, eps_sq, 0.01, float(self.G), levels,
                                                  L.ptr(table), st), "nb_build_level_table")
@@ -238,7 +238,8 @@ class GalaxySimulation:
         uni, m0 = L.uniform_mass(m) if mode in (PrecisionMode.FLOAT32, PrecisionMode.FLOAT64) else (False, 0.0)
         packed = buf.bytes(f"packed{code}", lib.nb_packed_bytes(n, dim, code))
         table = buf.bytes("level_table", lib.nb_level_table_bytes(levels)) if levels else None
-        ws = buf.bytes("accel_ws", lib.nb_accel_workspace_bytes(n, dim))
+        ws = buf.bytes("accel_ws", max(lib.nb_accel_workspace_bytes(n, dim),
+                                       lib.nb_max_dist_workspace_bytes(n) if levels else 0))
         with torch.cuda.device(x.device):
             L.check(lib.nb_run_ticks(L.ptr(x), L.ptr(v), L.ptr(a), L.ptr(m), n, dim, code, L.dtype_code(m),
                                      L.MODE_CODES[mode.value], levels, snap_levels, float(self.G), float(self.softening_sq),

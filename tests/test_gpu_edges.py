@@ -156,3 +156,46 @@ def test_empty_and_tiny_tensors_in_free_quantisers():
     np.testing.assert_array_equal(Q._grid_quantize(x64, 7).cpu().numpy(), ora.grid_quantize(x64.cpu(), 7).numpy())
     nc = torch.rand(64, 64, device=DEV).t()                               # non-contiguous input
     np.testing.assert_array_equal(Q._grid_quantize(nc, 16).cpu().numpy(), ora.grid_quantize(nc.cpu(), 16).numpy())
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("shape", ["disk", "shell", "cluster_far", "line", "grid", "two", "one"])
+def test_pruned_max_dist_is_bit_exact(shape, dim):
+    """nb_max_dist_sq (outer-shell candidates only) == brute-force max over all pairs of the reference's d²."""
+    import nbody_cosmological_simulation_b200 as nb
+    from nbody_cosmological_simulation_b200 import _lib as L
+    g = torch.Generator().manual_seed(hash(shape) % 1000 + dim)
+    n = {"two": 2, "one": 1}.get(shape, 3001)
+    if shape == "disk":
+        pos = torch.randn(n, dim, generator=g) * 3.0
+    elif shape == "shell":                      # every point is a candidate: worst case for the pruning
+        v = torch.randn(n, dim, generator=g)
+        pos = 7.0 * v / v.norm(dim=1, keepdim=True) + 100.0
+    elif shape == "cluster_far":                # far from the origin, tiny extent: fp32 cancellation in dx
+        pos = torch.randn(n, dim, generator=g) * 1e-3 + 4096.0
+    elif shape == "line":
+        pos = torch.zeros(n, dim); pos[:, 0] = torch.linspace(-5, 5, n)
+    elif shape == "grid":
+        pos = torch.randint(-4, 5, (n, dim), generator=g).float()
+    else:
+        pos = torch.randn(n, dim, generator=g)
+    pos = pos.float().to(DEV)
+    eps_sq = 0.1 ** 2
+    diff = pos.unsqueeze(0) - pos.unsqueeze(1)
+    want = ((diff ** 2).sum(dim=-1) + eps_sq).max().item()               # simulation.py:83-86 evaluated on the GPU by torch
+    lib = L.load()
+    mass = torch.ones(n, device=DEV)
+    packed = torch.empty(lib.nb_packed_bytes(n, dim, 0), dtype=torch.uint8, device=DEV)
+    scal = torch.empty(8, dtype=torch.int64, device=DEV)
+    ws = torch.empty(lib.nb_max_dist_workspace_bytes(n), dtype=torch.uint8, device=DEV)
+    st = L.stream_ptr(pos.device)
+    L.check(lib.nb_pack_sources(L.ptr(pos), L.ptr(mass), n, dim, 0, 0, L.ptr(packed), 0, st))
+    L.check(lib.nb_reset_scalars(L.ptr(scal), st))
+    L.check(lib.nb_max_dist_sq(L.ptr(packed), n, dim, 0, eps_sq, L.ptr(scal), L.ptr(ws), ws.numel(), st))
+    got = lib.nb_double_from_key(int(scal[0].item()))
+    assert got == want, (shape, got, want)
+    hdr = ws[:128].view(torch.int32)
+    count = int(hdr[7].item()) & 0xffffffff
+    assert 1 <= count <= n
+    if shape in ("disk", "cluster_far", "line"):
+        assert count < n // 4                                             # the pruning actually prunes
