@@ -26,6 +26,7 @@ struct AccelArgs {
     double eps_sq;
     const void* table;        // level table (Q_LUT)
     int levels;
+    int lut_rep;              // shared-memory replication of the level table (1, 2, 4 or 8 copies, see accel_kernel)
     float neg_zero;           // -0.0f, passed at run time so that the compiler cannot fold fma(d, d, -0) back into a mul
 };
 
@@ -67,6 +68,10 @@ struct ForceF32 {
         neg_zero = a.neg_zero;
         lut = lut_smem;
         if (QMODE == Q_LUT) {
+            // copy (lane mod rep) of every entry: the 8 lanes of an LDS.128 quarter-warp then hit 8 different 16-byte
+            // bank groups whatever their levels are (ncu: 3.0e9 bank conflicts per launch at L=256 without this)
+            lut = lut_smem + 1 + (threadIdx.x & (a.lut_rep - 1));
+            lut_stride = a.lut_rep;
             const float4 h = lut_smem[0];
             scale = h.y; min_val = h.z;
             lo2 = fmaf(-h.x, h.y, -0.5f + 1.0f / 64.0f);     // additive constant of the level estimate (see lut_factor)
@@ -102,10 +107,11 @@ struct ForceF32 {
         float kf = fmaf(lg2_approx(t), scale, lo2);                      // lo2 holds (−lo2·scale − ½ + margin), see init()
         kf = fminf(kf, levels_m1_f);
         const int k_lo = __float_as_int(kf + 12582912.0f) & 0x3fffff;
-        const float4 e = lut[1 + k_lo];
+        const float4 e = lut[k_lo * lut_stride];
         return t >= e.x ? e.z : e.y;
     }
     float levels_m1_f;
+    int lut_stride;
     int levels_m1;
 
     __device__ __forceinline__ void chunk(const unsigned char* s, int64_t) {
@@ -336,7 +342,8 @@ __global__ void __launch_bounds__(Consumer::THREADS + 32) accel_kernel(const Acc
         // the level table sits behind the streaming stages
         float4* dst = reinterpret_cast<float4*>(smem + stream_smem_bytes(Consumer::DIM));
         const float4* srcT = reinterpret_cast<const float4*>(a.table);
-        for (int k = threadIdx.x; k < a.levels + 1; k += blockDim.x) dst[k] = srcT[k];
+        if (threadIdx.x == 0) dst[0] = srcT[0];
+        for (int e = threadIdx.x; e < a.levels * a.lut_rep; e += blockDim.x) dst[1 + e] = srcT[1 + e / a.lut_rep];
         lut_smem = dst;
         __syncthreads();
     }
@@ -390,7 +397,11 @@ int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, 
     const int cap = max_splits_for(a.n_tgt, Consumer::DIM);
     if (max_by_ws > cap) max_by_ws = cap;
     int smem = stream_smem_bytes(Consumer::DIM);
-    if (USE_LUT) smem += (a.levels + 1) * 16;
+    if (USE_LUT) {
+        a.lut_rep = 8;                                        // as many copies as fit in 32 KB
+        while (a.lut_rep > 1 && a.levels * a.lut_rep * 16 > 32 * 1024) a.lut_rep >>= 1;
+        smem += (a.levels * a.lut_rep + 1) * 16;
+    }
     auto kern = accel_kernel<Consumer, USE_LUT>;
     int ctas_per_sm = 1;
     const int frc = kernel_occupancy((const void*)kern, Consumer::THREADS + 32, smem, &ctas_per_sm);
