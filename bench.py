@@ -218,7 +218,7 @@ def main():
 
     setattr(hook_obj, hook_name, timed_accel)
     for _ in range(W):
-        sim.run(1)
+        sim.step()
         flush_buf.zero_()
     force_events.clear()
     sampler = ClockSampler(local_rank)
@@ -230,7 +230,7 @@ def main():
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for _ in range(K):
-        sim.run(1)                               # kick-drift (+packed emit) -> [all-gather] -> force -> closing kick
+        sim.step()                               # kick-drift (+packed emit) -> [all-gather] -> force -> closing kick
         flush_buf.zero_()                        # L2 flush between steps
     stop.record()
     barrier()
@@ -261,7 +261,7 @@ def main():
         sim.velocities = host["v"].to(dev, non_blocking=True)
         sim.accelerations = host["a"].to(dev, non_blocking=True)
         sim.masses = host["m"].to(dev, non_blocking=True)
-        sim.run(1)
+        sim.step()
         host_out["x"].copy_(sim.positions, non_blocking=True)
         host_out["v"].copy_(sim.velocities, non_blocking=True)
         host_out["a"].copy_(sim.accelerations, non_blocking=True)
@@ -366,7 +366,7 @@ def main():
                 "cpu_baseline": cpu, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "note": "state uploaded from pinned host memory and downloaded again every step through "
-                                "GalaxySimulation (N=1) / ShardedGalaxySimulation attributes + run(1)"},
+                                "GalaxySimulation (N=1) / ShardedGalaxySimulation attributes + step()"},
                 "gpu_launches": launches}
         print(json.dumps(line), flush=True)
     if world > 1:
