@@ -291,27 +291,39 @@ def main():
                 hbm_peak = json.load(f).get("hbm_gbs")
         except Exception:
             pass
-        # fused kick-kick-drift + packed emit: one HBM round trip of the state, L2 flushed before each launch
-        x, v, m = sim._state()
-        a = sim.accelerations
-        ev = []
-        for i in range(12):
-            flush_buf.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            sim._kdk(L.KDK_KICK_KICK_DRIFT, x, v, a, m, emit_packed=True)
-            e1.record()
-            ev.append((e0, e1))
-        torch.cuda.synchronize()
-        kdk_ms = sorted(p.elapsed_time(q) for p, q in ev[2:])
-        kdk_ms = kdk_ms[len(kdk_ms) // 2]
-        sim._packed_key = None
-        kdk_bytes = N_PARTICLES * (3 * DIM * 4 + 2 * DIM * 4 + 4 + 16)     # read x,v,a + mass, write x,v + packed record
-        extra["kdk"] = {"kernel": "kdk_kernel<float,3,float,KICK_KICK_DRIFT>", "bound": "hbm", "bytes_per_launch": kdk_bytes,
-                        "ms": kdk_ms, "achieved": kdk_bytes / (kdk_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": (kdk_bytes / (kdk_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
+        # fused kick-kick-drift + packed emit: one HBM round trip of the state, L2 flushed before each
+        # launch; measured on the benchmark state (N = 2^20, 84 MB: latency-limited) and on a 16M-particle state
+        # (BASELINE.json configs[4], 1.3 GB >> L2), which is where this kernel's bandwidth matters
+        from nbody_cosmological_simulation_b200.ops import CudaOps
+        kops = CudaOps()
+
+        def kdk_rate(n_k):
+            xk, vk, ak = (torch.randn(n_k, DIM, device=dev) for _ in range(3))
+            mk = torch.ones(n_k, device=dev)
+            sk = kops.new_scalars(dev)
+            pk_ = torch.empty(kops.lib.nb_packed_bytes(n_k, DIM, 0), dtype=torch.uint8, device=dev)
+            ev = []
+            for i in range(10):
+                flush_buf.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                kops.kdk(L.KDK_KICK_KICK_DRIFT, xk, vk, ak, mk, DT, 0, sk, packed=pk_)
+                e1.record()
+                ev.append((e0, e1))
+            torch.cuda.synchronize()
+            ms = sorted(p.elapsed_time(q) for p, q in ev[2:])
+            ms = ms[len(ms) // 2]
+            nbytes = n_k * (3 * DIM * 4 + 2 * DIM * 4 + 4 + 16)     # read x,v,a + mass, write x,v + packed record
+            return ms, nbytes, nbytes / (ms * 1e-3) / 1e9
+
+        ms_s, by_s, gb_s = kdk_rate(N_PARTICLES)
+        ms_l, by_l, gb_l = kdk_rate(1 << 24)
+        extra["kdk"] = {"kernel": "kdk_vec_kernel<float,3,float,KICK_KICK_DRIFT>", "bound": "hbm", "n_particles": 1 << 24,
+                        "bytes_per_launch": by_l, "ms": ms_l, "achieved": gb_l, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": (gb_l / hbm_peak) if hbm_peak else None,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if hbm_peak else "unavailable",
-                        "note": "84 MB per launch: a 28 us kernel, latency- rather than bandwidth-limited at this N"}
+                        "at_benchmark_n": {"n_particles": N_PARTICLES, "bytes_per_launch": by_s, "ms": ms_s, "achieved": gb_s,
+                                           "note": "84 MB per launch, ~25 us: launch/DRAM-latency limited"}}
         # float64 state / FLOAT64 mode at the same N (the metric is quoted for fp64 and fp32)
         sim64 = nb.GalaxySimulation(pos.double().to(dev), vel.double().to(dev), mass.double().to(dev),
                                     precision_mode=nb.PrecisionMode.FLOAT64, G=G, softening=SOFTENING, dt=DT, device=dev)

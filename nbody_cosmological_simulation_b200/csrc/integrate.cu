@@ -139,6 +139,99 @@ __global__ void __launch_bounds__(256) kdk_kernel(const T* __restrict__ x_in, co
     }
 }
 
+// Vectorised variant: one thread owns TWO units (4 fp32 / 2 fp64 particles = 48 or 32 contiguous bytes per array),
+// so every array is moved with 16-byte LDG/STG (3 or 2 per array) instead of 4/8-byte accesses — the scalar
+// kernel above is LSU-instruction bound (2.6 TB/s at N = 2^20).  Requires 16-byte aligned base pointers; the last,
+// partially filled group and all padding units fall back to element-wise code inside the same kernel.
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { using type = float4; };
+template <> struct Vec16<double> { using type = double2; };
+
+template <typename T, int DIM, typename TM, int PHASE>
+__global__ void __launch_bounds__(256) kdk_vec_kernel(const T* __restrict__ x_in, const T* __restrict__ v_in, T* __restrict__ acc,
+                                                      T* __restrict__ x_out, T* __restrict__ v_out, int64_t n, T half_dt, T dt,
+                                                      int snap_levels, const int64_t* __restrict__ scalars,
+                                                      const TM* __restrict__ mass, char* __restrict__ packed, int64_t n_units) {
+    constexpr int UP = sizeof(T) == 4 ? 2 : 1;       // particles per unit
+    constexpr int PPT = 2 * UP;                      // particles per thread
+    constexpr int V = PPT * DIM;                     // values per thread and array
+    constexpr int EPV = 16 / sizeof(T);              // elements per 16-byte vector
+    constexpr int NV = V / EPV;                      // 3 (D=3) or 2 (D=2) vectors
+    using VT = typename Vec16<T>::type;
+    LinearGrid<T> grid(scalars, NB_SLOT_ACC_MIN, NB_SLOT_ACC_MAX, snap_levels > 0 ? snap_levels : 2);
+    const bool snap = snap_levels > 0;
+    const int64_t n_groups = (n_units + 1) / 2;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p0 = g * PPT;
+        const int64_t left = n - p0;
+        const int nreal = left >= PPT ? PPT : (left > 0 ? (int)left : 0);
+        const int64_t e0 = p0 * DIM;
+        T x[V], v[V], a[V];
+        if (nreal == PPT) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                reinterpret_cast<VT*>(a)[q] = reinterpret_cast<const VT*>(acc + e0)[q];
+                reinterpret_cast<VT*>(v)[q] = reinterpret_cast<const VT*>(v_in + e0)[q];
+                if (PHASE != NB_KDK_KICK) reinterpret_cast<VT*>(x)[q] = reinterpret_cast<const VT*>(x_in + e0)[q];
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const bool ok = e < nreal * DIM;
+                a[e] = ok ? acc[e0 + e] : (T)0;
+                v[e] = ok ? v_in[e0 + e] : (T)0;
+                x[e] = (ok && PHASE != NB_KDK_KICK) ? x_in[e0 + e] : (T)0;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            if (snap) a[e] = grid.snap(a[e]);
+            const T kick = mul_rn(a[e], half_dt);
+            v[e] = add_rn(v[e], kick);                                        // simulation.py:141 / :132
+            if (PHASE == NB_KDK_KICK_KICK_DRIFT) v[e] = add_rn(v[e], kick);   // :132 of the next tick
+            if (PHASE != NB_KDK_KICK) x[e] = add_rn(x[e], mul_rn(v[e], dt)); // :135
+        }
+        if (nreal == PPT) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                if (snap) reinterpret_cast<VT*>(acc + e0)[q] = reinterpret_cast<VT*>(a)[q];
+                reinterpret_cast<VT*>(v_out + e0)[q] = reinterpret_cast<VT*>(v)[q];
+                if (PHASE != NB_KDK_KICK) reinterpret_cast<VT*>(x_out + e0)[q] = reinterpret_cast<VT*>(x)[q];
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                if (e < nreal * DIM) {
+                    if (snap) acc[e0 + e] = a[e];
+                    v_out[e0 + e] = v[e];
+                    if (PHASE != NB_KDK_KICK) x_out[e0 + e] = x[e];
+                }
+            }
+        }
+        if (PHASE != NB_KDK_KICK && packed) {
+            const T far = sizeof(T) == 4 ? (T)kPadCoordF32 : (T)kPadCoordF64;
+            T pm[PPT];
+#pragma unroll
+            for (int h = 0; h < PPT; ++h) {
+                const bool real = h < nreal;
+                pm[h] = real ? (T)mass[p0 + h] : (T)0;
+                if (!real) {
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) x[h * DIM + k] = far;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int64_t unit = 2 * g + u;
+                if (unit < n_units) {
+                    if constexpr (sizeof(T) == 4) emit_unit_f32<DIM>(packed, unit, &x[(2 * u) * DIM], &x[(2 * u + 1) * DIM], pm[2 * u], pm[2 * u + 1]);
+                    else emit_unit_f64<DIM>(packed, unit, &x[u * DIM], pm[u]);
+                }
+            }
+        }
+    }
+}
+
 // ---- nb_snap_accelerations -------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) snap_kernel(T* __restrict__ acc, int64_t count, int levels,
@@ -174,9 +267,16 @@ int launch_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void*
     const int64_t natural = nb_num_chunks(n, sizeof(T) == 4 ? NB_F32 : NB_F64);
     if (packed && total_chunks != 0 && total_chunks < natural) return NB_ERR_INVALID_ARGUMENT;
     const int64_t n_units = packed ? (total_chunks ? total_chunks : natural) * kChunkUnits : (n + UP - 1) / UP;
-    kdk_kernel<T, DIM, TM, PHASE><<<grid_for(n_units, 256), 256, 0, st>>>(
-        (const T*)x_in, (const T*)v_in, (T*)acc, (T*)x_out, (T*)v_out, n, (T)(dt / 2), (T)dt, snap_levels, scalars,
-        (const TM*)mass, (char*)packed, n_units);
+    auto aligned16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    if (aligned16(x_in) && aligned16(v_in) && aligned16(acc) && aligned16(x_out) && aligned16(v_out)) {
+        kdk_vec_kernel<T, DIM, TM, PHASE><<<grid_for((n_units + 1) / 2, 256), 256, 0, st>>>(
+            (const T*)x_in, (const T*)v_in, (T*)acc, (T*)x_out, (T*)v_out, n, (T)(dt / 2), (T)dt, snap_levels, scalars,
+            (const TM*)mass, (char*)packed, n_units);
+    } else {
+        kdk_kernel<T, DIM, TM, PHASE><<<grid_for(n_units, 256), 256, 0, st>>>(
+            (const T*)x_in, (const T*)v_in, (T*)acc, (T*)x_out, (T*)v_out, n, (T)(dt / 2), (T)dt, snap_levels, scalars,
+            (const TM*)mass, (char*)packed, n_units);
+    }
     NB_CUDA_LAUNCH_CHECK();
     return NB_OK;
 }
