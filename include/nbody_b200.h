@@ -170,11 +170,12 @@ int nb_run_ticks(void* x, void* v, void* acc, const void* mass, int64_t n, int d
 
 /* ---- energies: simulation.py:170-196 ------------------------------------------------------- */
 int64_t nb_energy_workspace_bytes(int64_t n_targets);
-/* out[0] = Σ_{i in targets} m_i Σ_{j≠i} m_j / sqrt(d²_ij)   (double; caller applies −G/2 and sums ranks).
- * The targets must be members of the source set (an i-range shard of it): the j == i term is removed
- * by subtracting the identical expression once per target. */
+/* out[0] = Σ_{i in targets} Σ_{j > i} m_i m_j / sqrt(d²_ij)  over UNORDERED pairs (double; the caller applies −G
+ * and sums ranks).  The targets must be the sources tgt_offset .. tgt_offset+n_tgt−1 of the packed set (an i-range
+ * shard).  With a chunk-aligned tgt_offset only the upper triangle is evaluated (half the pairs); a negative or
+ * unaligned offset selects the full-matrix form ½ Σ_{j≠i}, which needs no index correspondence. */
 int nb_potential_energy(const void* packed_src, int64_t n_src, const void* pos_tgt, const void* mass_tgt,
-                        int64_t n_tgt, int dim, int dtype, int mass_dtype, double eps_sq,
+                        int64_t n_tgt, int64_t tgt_offset, int dim, int dtype, int mass_dtype, double eps_sq,
                         double* out, void* workspace, int64_t workspace_bytes, void* stream);
 /* out[0] = Σ_i m_i Σ_k v_ik²  (double; caller applies 0.5). */
 int nb_kinetic_energy(const void* vel, const void* mass, int64_t n, int dim, int dtype, int mass_dtype,

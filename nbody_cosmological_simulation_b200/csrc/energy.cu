@@ -19,7 +19,8 @@ struct PotentialF32 {
     static constexpr int THREADS = THREADS_;
     float2 nx[IPT], ny[IPT], nz[IPT];
     float2 acc[IPT];
-    double sum[IPT];
+    double sum[IPT], sum_diag[IPT];          // chunks strictly above the diagonal square / chunks inside it
+    int64_t diag_lo, diag_hi;                // chunk range of this CTA's diagonal square
     float2 eps2;
     __device__ __forceinline__ void init(const float* pos, int64_t n_tgt, float e2) {
 #pragma unroll
@@ -29,11 +30,11 @@ struct PotentialF32 {
             const float x = pos[i * DIM + 0], y = pos[i * DIM + 1], z = DIM == 3 ? pos[i * DIM + 2] : 0.f;
             nx[t] = make_float2(-x, -x); ny[t] = make_float2(-y, -y); nz[t] = make_float2(-z, -z);
             acc[t] = make_float2(0.f, 0.f);
-            sum[t] = 0.0;
+            sum[t] = sum_diag[t] = 0.0;
         }
         eps2 = make_float2(e2, e2);
     }
-    __device__ __forceinline__ void chunk(const unsigned char* s, int64_t) {
+    __device__ __forceinline__ void chunk(const unsigned char* s, int64_t chunk_index) {
         const float4* A = reinterpret_cast<const float4*>(s);
         const float4* B4 = reinterpret_cast<const float4*>(s + kChunkABytes);
         const float2* B2 = reinterpret_cast<const float2*>(s + kChunkABytes);
@@ -54,8 +55,13 @@ struct PotentialF32 {
                 acc[t] = fma2(ms, r, acc[t]);
             }
         }
+        const bool diag = chunk_index >= diag_lo && chunk_index < diag_hi;
 #pragma unroll
-        for (int t = 0; t < IPT; ++t) { sum[t] += (double)(acc[t].x + acc[t].y); acc[t] = make_float2(0.f, 0.f); }
+        for (int t = 0; t < IPT; ++t) {
+            const double c = (double)(acc[t].x + acc[t].y);
+            if (diag) sum_diag[t] += c; else sum[t] += c;
+            acc[t] = make_float2(0.f, 0.f);
+        }
     }
 };
 
@@ -71,7 +77,8 @@ struct PotentialF64 {
     static constexpr int DIM = DIM_;
     static constexpr int THREADS = THREADS_;
     double xi[IPT], yi[IPT], zi[IPT];
-    double sum[IPT];
+    double sum[IPT], sum_diag[IPT];
+    int64_t diag_lo, diag_hi;
     double eps2;
     __device__ __forceinline__ void init(const double* pos, int64_t n_tgt, double e2) {
 #pragma unroll
@@ -79,14 +86,17 @@ struct PotentialF64 {
             int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i >= n_tgt) i = n_tgt - 1;
             xi[t] = pos[i * DIM + 0]; yi[t] = pos[i * DIM + 1]; zi[t] = DIM == 3 ? pos[i * DIM + 2] : 0.0;
-            sum[t] = 0.0;
+            sum[t] = sum_diag[t] = 0.0;
         }
         eps2 = e2;
     }
-    __device__ __forceinline__ void chunk(const unsigned char* s, int64_t) {
+    __device__ __forceinline__ void chunk(const unsigned char* s, int64_t chunk_index) {
         const double2* A = reinterpret_cast<const double2*>(s);
         const double2* B2 = reinterpret_cast<const double2*>(s + kChunkABytes);
         const double* B1 = reinterpret_cast<const double*>(s + kChunkABytes);
+        double part[IPT];
+#pragma unroll
+        for (int t = 0; t < IPT; ++t) part[t] = 0.0;
 #pragma unroll 2
         for (int p = 0; p < kChunkUnits; ++p) {
             const double2 a = A[p];
@@ -98,25 +108,43 @@ struct PotentialF64 {
                 double d2 = fma(dx, dx, eps2);
                 d2 = fma(dy, dy, d2);
                 if (DIM == 3) { const double dz = zs - zi[t]; d2 = fma(dz, dz, d2); }
-                sum[t] = fma(m, rsqrt_full(d2), sum[t]);
+                part[t] = fma(m, rsqrt_full(d2), part[t]);
             }
         }
+        const bool diag = chunk_index >= diag_lo && chunk_index < diag_hi;
+#pragma unroll
+        for (int t = 0; t < IPT; ++t) { if (diag) sum_diag[t] += part[t]; else sum[t] += part[t]; }
     }
 };
 
 template <typename T, typename TM, int DIM, int IPT, int THREADS>
 __global__ void __launch_bounds__(THREADS + 32) potential_kernel(const char* __restrict__ src, int64_t n_chunks,
                                                                  const T* __restrict__ pos_tgt, const TM* __restrict__ mass_tgt,
-                                                                 int64_t n_tgt, int chunks_per_split, double eps_sq,
+                                                                 int64_t n_tgt, int64_t tgt_offset, int triangular,
+                                                                 int chunks_per_split, double eps_sq,
                                                                  double* __restrict__ block_partials) {
+    // Unordered pairs: out = Σ_{i<j} m_i m_j / r_ij.  With chunk-aligned targets (triangular != 0) a CTA skips every
+    // source chunk below its own targets, counts chunks above them once, and counts the diagonal square (sources that
+    // are its own targets) with weight ½ after removing the j == i term.  Otherwise every chunk is "diagonal":
+    // ½ Σ_{j≠i}, the reference's full-matrix form.
     __shared__ double red[32];
+    constexpr int TB = THREADS * IPT;
+    constexpr int CS = sizeof(T) == 4 ? 2 * kChunkUnits : kChunkUnits;       // sources per chunk
+    static_assert(TB % CS == 0, "a target block must cover whole chunks");
     using Cons = typename std::conditional<sizeof(T) == 4, PotentialF32<DIM, IPT, THREADS>, PotentialF64<DIM, IPT, THREADS>>::type;
     Cons cons;
     const bool is_consumer = threadIdx.x < THREADS;
     if (is_consumer) cons.init(pos_tgt, n_tgt, (T)eps_sq);
-    const int64_t c0 = (int64_t)blockIdx.y * chunks_per_split;
+    int64_t c0 = (int64_t)blockIdx.y * chunks_per_split;
     const int64_t c1 = min(n_chunks, c0 + (int64_t)chunks_per_split);
-    stream_sources(src, c0, c1, cons);
+    const int64_t first_tgt = tgt_offset + (int64_t)blockIdx.x * TB;
+    cons.diag_lo = triangular ? first_tgt / CS : 0;
+    // the diagonal square ends with this block's REAL targets (a partial last block must not claim the chunks of the
+    // next rank's slot); the tail of its last chunk is padding (mass 0)
+    const int64_t blk_tgts = min((int64_t)TB, n_tgt - (int64_t)blockIdx.x * TB);
+    cons.diag_hi = triangular ? (first_tgt + blk_tgts + CS - 1) / CS : n_chunks;
+    if (c0 < cons.diag_lo) c0 = cons.diag_lo;                         // pairs with j < i are counted by the other side
+    stream_sources(src, c0, c1 > c0 ? c1 : c0, cons);
     double mine = 0.0;
     if (is_consumer) {
 #pragma unroll
@@ -124,14 +152,15 @@ __global__ void __launch_bounds__(THREADS + 32) potential_kernel(const char* __r
             const int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i < n_tgt) {
                 const double m = (double)mass_tgt[i];
-                double s = cons.sum[t];
-                if (blockIdx.y == 0) {       // the self term lives in exactly one j-split: remove it once
+                double sd = cons.sum_diag[t];
+                const int64_t self_chunk = (tgt_offset + i) / CS;      // the j == i term lives in exactly one j-split
+                if (self_chunk >= c0 && self_chunk < c1) {
                     double self;
                     if constexpr (sizeof(T) == 4) self = (double)((float)m * rsqrt_approx((float)eps_sq));
                     else self = m * rsqrt_full(eps_sq);
-                    s -= self;
+                    sd -= self;
                 }
-                mine += m * s;
+                mine += m * (cons.sum[t] + 0.5 * sd);
             }
         }
     }
@@ -245,7 +274,7 @@ extern "C" int64_t nb_energy_workspace_bytes(int64_t n_targets) {
 
 template <typename T, typename TM, int DIM>
 static int launch_potential(const void* packed_src, int64_t n_src, const void* pos_tgt, const void* mass_tgt, int64_t n_tgt,
-                            int dtype, double eps_sq, double* out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+                            int64_t tgt_offset, int dtype, double eps_sq, double* out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
     constexpr int TH = 256, IPT = 2;
     const int64_t n_chunks = nb_num_chunks(n_src, dtype);
     auto k = potential_kernel<T, TM, DIM, IPT, TH>;
@@ -257,8 +286,9 @@ static int launch_potential(const void* packed_src, int64_t n_src, const void* p
     const int blocks_i = sp.blocks_i, cps = sp.chunks_per_split, splits = sp.splits;
     const int64_t ctas = (int64_t)blocks_i * splits;
     if (workspace_bytes < ctas * (int64_t)sizeof(double)) return NB_ERR_WORKSPACE_TOO_SMALL;
+    const int triangular = tgt_offset >= 0 && tgt_offset % nb_chunk_sources(dtype) == 0;
     k<<<dim3(blocks_i, splits), TH + 32, smem, st>>>((const char*)packed_src, n_chunks, (const T*)pos_tgt, (const TM*)mass_tgt, n_tgt,
-                                                    cps, eps_sq, (double*)workspace);
+                                                    triangular ? tgt_offset : 0, triangular, cps, eps_sq, (double*)workspace);
     NB_CUDA_LAUNCH_CHECK();
     final_sum_kernel<<<1, 1024, 0, st>>>((const double*)workspace, ctas, out);
     NB_CUDA_LAUNCH_CHECK();
@@ -266,14 +296,14 @@ static int launch_potential(const void* packed_src, int64_t n_src, const void* p
 }
 
 extern "C" int nb_potential_energy(const void* packed_src, int64_t n_src, const void* pos_tgt, const void* mass_tgt, int64_t n_tgt,
-                                   int dim, int dtype, int mass_dtype, double eps_sq, double* out, void* workspace,
+                                   int64_t tgt_offset, int dim, int dtype, int mass_dtype, double eps_sq, double* out, void* workspace,
                                    int64_t workspace_bytes, void* stream) {
     if (!packed_src || !pos_tgt || !mass_tgt || !out || !workspace || n_src <= 0 || n_tgt <= 0 || (dim != 2 && dim != 3))
         return NB_ERR_INVALID_ARGUMENT;
     cudaStream_t st = (cudaStream_t)stream;
 #define NB_PE_CASE(T, DT, TM, MDT, D) \
     if (dtype == DT && mass_dtype == MDT && dim == D) \
-        return launch_potential<T, TM, D>(packed_src, n_src, pos_tgt, mass_tgt, n_tgt, dtype, eps_sq, out, workspace, workspace_bytes, st);
+        return launch_potential<T, TM, D>(packed_src, n_src, pos_tgt, mass_tgt, n_tgt, tgt_offset, dtype, eps_sq, out, workspace, workspace_bytes, st);
     NB_PE_CASE(float, NB_F32, float, NB_F32, 2) NB_PE_CASE(float, NB_F32, float, NB_F32, 3)
     NB_PE_CASE(float, NB_F32, double, NB_F64, 2) NB_PE_CASE(float, NB_F32, double, NB_F64, 3)
     NB_PE_CASE(double, NB_F64, float, NB_F32, 2) NB_PE_CASE(double, NB_F64, float, NB_F32, 3)

@@ -104,14 +104,14 @@ class CudaOps:
             L.check(self.lib.nb_snap_accelerations(L.ptr(acc), acc.numel(), L.dtype_code(acc), int(levels), L.ptr(scalars),
                                                    L.stream_ptr(acc.device)), "nb_snap_accelerations")
 
-    def potential(self, packed, n_src, x_tgt, m_tgt, eps_sq):
+    def potential(self, packed, n_src, x_tgt, m_tgt, eps_sq, tgt_offset=0):
         L.require_cuda(packed, x_tgt, m_tgt)
         n, dim = x_tgt.shape
         out = torch.empty(1, dtype=torch.float64, device=x_tgt.device)
         ws = self._scratch("energy", self.lib.nb_energy_workspace_bytes(n), x_tgt.device)
         with torch.cuda.device(x_tgt.device):
-            L.check(self.lib.nb_potential_energy(L.ptr(packed), int(n_src), L.ptr(x_tgt), L.ptr(m_tgt), n, dim,
-                                                 L.dtype_code(x_tgt), L.dtype_code(m_tgt), float(eps_sq), L.ptr(out),
+            L.check(self.lib.nb_potential_energy(L.ptr(packed), int(n_src), L.ptr(x_tgt), L.ptr(m_tgt), n, int(tgt_offset),
+                                                 dim, L.dtype_code(x_tgt), L.dtype_code(m_tgt), float(eps_sq), L.ptr(out),
                                                  L.ptr(ws), ws.numel(), L.stream_ptr(x_tgt.device)), "nb_potential_energy")
         return out
 

@@ -221,13 +221,31 @@ class ShardedGalaxySimulation:
     def get_potential_energy(self) -> float:
         x = self.positions.contiguous()
         packed, n_src = self._sources_for(x)
-        s = self.ops.potential(packed, n_src, x, self.masses, self.softening_sq)
+        plan = self._plan_for(x.dtype)
+        offset = self.rank * plan.slot_chunks * plan.chunk_sources        # first local target inside the padded source set
+        s = self.ops.potential(packed, n_src, x, self.masses, self.softening_sq, tgt_offset=offset)
         self._all_reduce(s, dist.ReduceOp.SUM)
-        val = -float(self.G) * 0.5 * s.item()
+        val = -float(self.G) * s.item()
         return float(np.float32(val)) if x.dtype == torch.float32 else float(val)
 
     def get_total_energy(self) -> float:
         return self.get_kinetic_energy() + self.get_potential_energy()
+
+    def collect_metrics(self, tick: int, metrics) -> None:
+        """`metrics.collect_metrics` (reference metrics.py:159-179) for a sharded run: the O(N²) energies use the
+        sharded reductions; the O(N log N) remainder (radius percentile, bound fraction, dispersion, rotation curve)
+        runs on the gathered state, identically on every rank, so every rank appends the same values."""
+        from . import metrics as M
+        pos, vel, mass = self.gather(self.positions), self.gather(self.velocities), self.gather(self.masses)
+        metrics.ticks.append(tick)
+        ke, pe = self.get_kinetic_energy(), self.get_potential_energy()
+        metrics.kinetic_energy.append(ke)
+        metrics.potential_energy.append(pe)
+        metrics.total_energy.append(ke + pe)
+        metrics.galaxy_radius_90.append(M.compute_galaxy_radius(pos, 90))
+        metrics.bound_fraction.append(M.compute_bound_fraction(pos, vel, mass, self.G))
+        metrics.velocity_dispersion.append(M.compute_velocity_dispersion(vel))
+        metrics.rotation_curves.append(M.compute_rotation_curve(pos, vel))
 
     def gather(self, local: torch.Tensor) -> torch.Tensor:
         """Full (N, …) tensor from the local slices (variable slice sizes -> padded all_gather)."""

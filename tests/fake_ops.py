@@ -153,11 +153,11 @@ class FakeOps:
             scalars[L.SLOT_ACC_MAX] = max(int(scalars[L.SLOT_ACC_MAX]), key(acc.max().item()))
         return acc
 
-    def potential(self, packed, n_src, x_tgt, m_tgt, eps_sq):
+    def potential(self, packed, n_src, x_tgt, m_tgt, eps_sq, tgt_offset=0):
         _, d2, m = self._pairs(packed, n_src, x_tgt, eps_sq)
         inv = 1.0 / torch.sqrt(d2.double())
         s = (m.double().unsqueeze(0) * inv).sum(dim=1) - m_tgt.double() / (float(torch.tensor(eps_sq, dtype=x_tgt.dtype)) ** 0.5)
-        return (m_tgt.double() * s).sum().reshape(1)
+        return (0.5 * (m_tgt.double() * s).sum()).reshape(1)          # unordered pairs: ½ Σ_{j≠i} summed over ranks
 
     def kinetic(self, v, m):
         return (m.double() * (v.double() ** 2).sum(dim=-1)).sum().reshape(1)

@@ -39,6 +39,8 @@ def main():
         st = sh.get_state()
         acc = sh.gather(sh.accelerations)
         e1 = sh.get_total_energy()
+        ms = nb.SimulationMetrics()
+        sh.collect_metrics(sh.tick, ms)                       # collective: every rank takes part
         if rank == 0:
             one = nb.GalaxySimulation(pos, vel, mass, precision_mode=pm)
             f0 = one.get_total_energy()
@@ -55,6 +57,11 @@ def main():
                 good = da <= tol * 10 and dx <= tol * 20 and dv <= tol * 20
             good = good and abs(e0 - f0) <= 1e-6 * abs(f0) and abs(e1 - f1) <= (1e-3 if "int" in mode else 1e-6) * abs(f1)
             good = good and st["positions"].dtype == one.positions.dtype and sh.tick == one.tick
+            m1 = nb.SimulationMetrics()
+            nb.collect_metrics(one, one.tick, m1)
+            same_rc = ms.rotation_curves[0]["num_stars_per_bin"] == m1.rotation_curves[0]["num_stars_per_bin"]
+            good = good and same_rc and ms.galaxy_radius_90 == m1.galaxy_radius_90 and ms.bound_fraction == m1.bound_fraction \
+                and abs(ms.total_energy[0] - m1.total_energy[0]) <= (1e-3 if "int" in mode else 1e-6) * abs(m1.total_energy[0])
             print(f"world={world} N={n} D={dim} {mode:9s} {str(dtype):14s} dpos={dx:.2e} dvel={dv:.2e} dacc={da:.2e} "
                   f"E0 {e0:.8g}/{f0:.8g} E1 {e1:.8g}/{f1:.8g} counts={sh.plan.count[:3]}... {'OK' if good else 'MISMATCH'}", flush=True)
             ok = ok and good
