@@ -3,9 +3,10 @@
 //
 // Roofline: FP32 (FMA pipe) / FP64 (DFMA pipe) issue-bound, 0 algorithmic HBM bytes per pair: the
 // packed source set (16 B per fp32 particle) is L2-resident and streamed through shared memory.
-//   fp32, D=3: per source PAIR and target 12 packed fp32x2 ops (FADD2/FFMA2/FMUL2 = 24 FMA-pipe
-//   cycles per warp) + 2 MUFU.RSQ;  D=2: 9 packed ops + 2 MUFU.RSQ.
-//   fp64, D=3: 16 DFMA-class ops + 1 MUFU.RSQ64H per pair (seed + one cubic-corrected Newton step).
+//   fp32, D=3: per source PAIR and target 12 packed fp32x2 ops (11 when all masses are equal) + 2 MUFU.RSQ;
+//   D=2: 9 (8) packed ops + 2 MUFU.RSQ.  Ops with <= 2 distinct register pairs issue in 2 cycles, the three
+//   accumulate FFMA2 (3 distinct pairs) in 3: floor 25 cycles per 64 interactions per SM sub-partition.
+//   fp64, D=3: 16 (15) DFMA-class ops + 1 MUFU.RSQ64H per pair (seed + one cubic-corrected Newton step).
 // Accumulation: per-thread fp32x2 partial sums over one chunk (256 sources), flushed into fp64
 // accumulators per chunk => the Σ_j error does not grow with N (SURVEY.md §7 "hard parts").
 #include <cuda_fp16.h>
@@ -31,8 +32,8 @@ struct AccelArgs {
 };
 
 // Level table layout (Q_LUT): float4 entry[k] = { T_{k+1}, g_k, g_{k+1}, 0 } for k = 0..L-1, preceded by a
-// 16-byte header { lo2 (log2 of lower bound), scale (levels-1)/(hi2-lo2), min_val, degenerate flag }.
-struct LevelHeader { float lo2, scale, min_val, degenerate; };
+// 16-byte header { lo2 (log2 of lower bound), scale (levels-1)/(hi2-lo2), min_val, degenerate flag }
+// (written by build_level_table_kernel in quantize.cu).
 
 // ======================================================================================================
 // fp32 state, packed-pair arithmetic
@@ -112,7 +113,6 @@ struct ForceF32 {
     }
     float levels_m1_f;
     int lut_stride;
-    int levels_m1;
 
     __device__ __forceinline__ void chunk(const unsigned char* s, int64_t) {
         const float4* A = reinterpret_cast<const float4*>(s);
