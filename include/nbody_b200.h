@@ -155,15 +155,17 @@ int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_o
            int dtype, double dt, int phase, int snap_levels, const int64_t* scalars,
            const void* mass, int mass_dtype, void* packed_out, int64_t total_chunks, void* stream);
 
-/* GalaxySimulation.run for the stock force (simulation.py:145-158): `ticks` leapfrog ticks in one call, in place
- * on x, v (n, dim) and acc (n, dim; must hold the current, already snapped accelerations and have the state
- * dtype).  Per tick: nb_kdk(KICK_KICK_DRIFT, emitting `packed`) -> [int modes: nb_reset_scalars, nb_max_dist_sq,
+/* GalaxySimulation.run for the stock force (simulation.py:145-158): `ticks` leapfrog ticks in one call.  The first
+ * tick reads x_in, v_in, acc_in (the current state; acc_in already snapped, state dtype) and writes x, v, acc; later
+ * ticks update x, v, acc in place.  Pass NULL for the *_in pointers to run fully in place.  The reference rebinds
+ * its attributes to new tensors every tick: giving fresh x, v, acc buffers reproduces that without copies.  Per tick: nb_kdk(KICK_KICK_DRIFT, emitting `packed`) -> [int modes: nb_reset_scalars, nb_max_dist_sq,
  * nb_build_level_table] -> nb_accel; a closing nb_kdk(KICK) leaves a consistent, observable state.  Bit-identical
  * to issuing those calls one by one.  levels = d² grid levels (0 for float modes), snap_levels = force grid levels
  * (INT8/INT4, else 0).  use_graph != 0 captures the tick body once into a CUDA graph and replays it (worth it for
  * small systems where launch latency dominates).  packed: nb_packed_bytes; level_table: nb_level_table_bytes (or
  * NULL); workspace: max(nb_accel_workspace_bytes, nb_max_dist_workspace_bytes) — the two uses never overlap. */
-int nb_run_ticks(void* x, void* v, void* acc, const void* mass, int64_t n, int dim, int dtype, int mass_dtype,
+int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_in, void* x, void* v, void* acc,
+                 const void* mass, int64_t n, int dim, int dtype, int mass_dtype,
                  int mode, int levels, int snap_levels, double G, double eps_sq, double min_dist_sq, double dt,
                  int64_t ticks, int uniform_mass, double mass_value, void* packed, void* level_table,
                  int64_t* scalars, void* workspace, int64_t workspace_bytes, int use_graph, void* stream);

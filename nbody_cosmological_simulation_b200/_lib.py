@@ -45,7 +45,7 @@ PROTOTYPES = {
                          _P, _P, _P, c_int64, _P]),
     "nb_snap_accelerations": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     "nb_kdk": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_double, c_int, c_int, _P, _P, c_int, _P, c_int64, _P]),
-    "nb_run_ticks": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
+    "nb_run_ticks": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
                              c_double, c_int64, c_int, c_double, _P, _P, _P, _P, c_int64, c_int, _P]),
     "nb_energy_workspace_bytes": (c_int64, [c_int64]),
     "nb_potential_energy": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_double, _P, _P, c_int64, _P]),

@@ -10,6 +10,7 @@ using namespace nb;
 namespace {
 
 struct TickArgs {
+    const void *x_in, *v_in; void* acc_in;     // state read by the FIRST tick (== x, v, acc for an in-place run)
     void *x, *v, *acc; const void* mass; int64_t n; int dim, dtype, mass_dtype, mode, levels, snap_levels;
     double G, eps_sq, min_dist_sq, dt; int uniform; double mass_value;
     void *packed, *table; int64_t* scalars; void* ws; int64_t ws_bytes;
@@ -18,7 +19,7 @@ struct TickArgs {
 // one tick body: [closing kick of the previous tick +] opening kick + drift (+ packed emit), then the force
 int enqueue_tick(const TickArgs& a, bool first, cudaStream_t st) {
     const int phase = first ? NB_KDK_KICK_DRIFT : NB_KDK_KICK_KICK_DRIFT;
-    int rc = nb_kdk(a.x, a.v, a.acc, a.x, a.v, a.n, a.dim, a.dtype, a.dt, phase, first ? 0 : a.snap_levels, a.scalars, a.mass,
+    int rc = nb_kdk(first ? a.x_in : a.x, first ? a.v_in : a.v, first ? a.acc_in : a.acc, a.x, a.v, a.n, a.dim, a.dtype, a.dt, phase, first ? 0 : a.snap_levels, a.scalars, a.mass,
                     a.mass_dtype, a.packed, 0, st);
     if (rc) return rc;
     if (a.levels > 0) {
@@ -33,14 +34,15 @@ int enqueue_tick(const TickArgs& a, bool first, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" int nb_run_ticks(void* x, void* v, void* acc, const void* mass, int64_t n, int dim, int dtype, int mass_dtype, int mode,
+extern "C" int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_in, void* x, void* v, void* acc, const void* mass, int64_t n, int dim, int dtype, int mass_dtype, int mode,
                             int levels, int snap_levels, double G, double eps_sq, double min_dist_sq, double dt, int64_t ticks,
                             int uniform_mass, double mass_value, void* packed, void* level_table, int64_t* scalars,
                             void* workspace, int64_t workspace_bytes, int use_graph, void* stream) {
     if (!x || !v || !acc || !mass || !packed || !scalars || !workspace || n <= 0 || ticks < 0) return NB_ERR_INVALID_ARGUMENT;
     if (ticks == 0) return NB_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    TickArgs a{x, v, acc, mass, n, dim, dtype, mass_dtype, mode, levels, snap_levels, G, eps_sq, min_dist_sq, dt,
+    // the first kick only reads acc_in (it is already snapped, so no snap/write-back happens on it)
+    TickArgs a{x_in ? x_in : x, v_in ? v_in : v, acc_in ? const_cast<void*>(acc_in) : acc, x, v, acc, mass, n, dim, dtype, mass_dtype, mode, levels, snap_levels, G, eps_sq, min_dist_sq, dt,
                uniform_mass, mass_value, packed, level_table, scalars, workspace, workspace_bytes};
     int rc = enqueue_tick(a, /*first=*/true, st);
     if (rc) return rc;

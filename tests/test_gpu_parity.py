@@ -149,13 +149,20 @@ def test_twenty_ticks(golden, mode):
 def test_step_equals_fused_run(golden):
     """step() (observable state every tick) and run() (closing kick fused into the next tick) are bit-identical."""
     g = golden("disk256_modes")
-    for mode in ("float32", "int4_sim", "float64"):
-        a, b = make_sim(g, mode), make_sim(g, mode)
+    for mode in ("float32", "int4_sim", "int8_sim", "float16", "float64"):
+        a, b, c = make_sim(g, mode), make_sim(g, mode), make_sim(g, mode)
+        c._explicit_step = True                  # four separate C-ABI calls per tick from Python
+        held = a.positions
+        before = held.clone()
         for _ in range(7):
-            a.step()
-        b.run(7)
-        assert torch.equal(a.positions, b.positions) and torch.equal(a.velocities, b.velocities), mode
-        assert torch.equal(a.accelerations, b.accelerations), mode
+            a.step()                             # one native call per tick
+            c.step()
+        b.run(7)                                 # one native call, CUDA-graph replay of the fused tick
+        assert torch.equal(held, before)         # tensors handed out earlier are never written
+        for other in (b, c):
+            assert torch.equal(a.positions, other.positions) and torch.equal(a.velocities, other.velocities), mode
+            assert torch.equal(a.accelerations, other.accelerations), mode
+        assert a.tick == b.tick == c.tick == 7
 
 
 def test_rotation_curve_and_metrics(golden):
