@@ -191,6 +191,18 @@ int nb_radius_max(const void* pos, int64_t n, int dim, int dtype, int64_t* scala
 int nb_rotation_curve(const void* pos, const void* vel, int64_t n, int dim, int dtype, const void* edges,
                       int num_bins, double* sum_vt, int64_t* count, void* stream);
 
+/* ---- remainder of collect_metrics: metrics.py:81-95, 148-156 -------- */
+int64_t nb_metrics_workspace_bytes(void);
+/* compute_galaxy_radius: out[0] (state dtype, device) = k-th smallest (0-based) of sqrt(Σ_k x_ik²), found by
+ * MSB-first radix select over the float bit patterns — bit-identical to torch.sort(radii)[0][k], no sort. */
+int nb_radius_kth(const void* pos, int64_t n, int dim, int dtype, int64_t k, void* out, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+/* compute_velocity_dispersion: with s_i = |v_i| − |v_0| (shifted by the first star's speed for conditioning),
+ * out[0] = Σ_i s_i, out[1] = Σ_i s_i² (doubles, device); the caller forms the unbiased standard deviation
+ * sqrt((out[1] − out[0]²/n)/(n−1)), which is invariant under the shift. */
+int nb_speed_moments(const void* vel, int64_t n, int dim, int dtype, double* out, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+
 /* ---- free-standing quantisers: quantization.py:74-127 -------------------------------------- */
 int nb_reset_scalars(int64_t* scalars, void* stream);
 /* scalars[VAL_MIN/VAL_MAX] = min/max of `in` (after clamp(min=clamp_min) and log() when log_space). */

@@ -52,6 +52,9 @@ PROTOTYPES = {
     "nb_kinetic_energy": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, _P, c_int64, _P]),
     "nb_radius_max": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     "nb_rotation_curve": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, _P, _P, _P]),
+    "nb_metrics_workspace_bytes": (c_int64, []),
+    "nb_radius_kth": (c_int, [_P, c_int64, c_int, c_int, c_int64, _P, _P, c_int64, _P]),
+    "nb_speed_moments": (c_int, [_P, c_int64, c_int, c_int, _P, _P, c_int64, _P]),
     "nb_reset_scalars": (c_int, [_P, _P]),
     "nb_tensor_minmax": (c_int, [_P, c_int64, c_int, c_int, c_double, _P, _P]),
     "nb_grid_quantize": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P]),

@@ -1,14 +1,16 @@
-"""Metrics — the API of the reference's metrics.py.
+"""Metrics — the API of the reference's metrics.py, on sm_100a kernels.
 
-On the hot path named by BASELINE.json: `compute_rotation_curve`, which here is
-one radius-max reduction plus one binned sum/count kernel and two host reads instead of ~3·bins+1
-synchronising masked reductions (metrics.py:48-78), and `collect_metrics`, whose O(N²) potential
-energy goes through `GalaxySimulation.get_potential_energy` (sm_100a pair kernel).
-`compute_galaxy_radius`, `compute_bound_fraction` and `compute_velocity_dispersion` are the O(N log N)
-remainder that SURVEY.md §8f ranks "next": they stay device-side torch sort/cumsum/std calls.
+On the hot path named by BASELINE.json: `compute_rotation_curve` — one radius-max reduction
+plus one binned sum/count kernel and two host reads instead of ~3·bins+1 synchronising masked reductions
+(metrics.py:48-78) — and `collect_metrics`, whose O(N²) potential energy goes through
+`GalaxySimulation.get_potential_energy` (upper-triangle pair kernel, cached per state).
+The O(N) remainder that SURVEY.md §8f ranks "next" is widened here too: `compute_galaxy_radius` is an exact radix
+select (no sort) and `compute_velocity_dispersion` a one-pass fp64 moment reduction; `compute_bound_fraction` needs
+the rank of every star in radius order and stays a device-side torch sort/cumsum.
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -30,6 +32,15 @@ class SimulationMetrics:
     rotation_curves: list = field(default_factory=list)
 
 
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous CUDA fp32/fp64 (N, 2|3) view of a state tensor, or a loud error."""
+    L.require_cuda(t)
+    L.dtype_code(t)
+    if t.dim() != 2 or t.shape[1] not in (2, 3):
+        raise L.NbodyLibraryError(f"expected an (N, 2) or (N, 3) tensor, got {tuple(t.shape)}")
+    return t.contiguous()
+
+
 def compute_rotation_curve(positions: torch.Tensor, velocities: torch.Tensor, num_bins: int = 20,
                            max_radius: float = None) -> dict:
     """Mean tangential speed in `num_bins` half-open radial bins (reference metrics.py:25-78).
@@ -40,7 +51,7 @@ def compute_rotation_curve(positions: torch.Tensor, velocities: torch.Tensor, nu
     """
     L.require_cuda(positions, velocities)
     dt = torch.promote_types(positions.dtype, velocities.dtype)
-    pos, vel = positions.contiguous().to(dt), velocities.contiguous().to(dt)
+    pos, vel = _rows(positions.to(dt)), _rows(velocities.to(dt))
     code = L.dtype_code(pos)
     n, dim = pos.shape
     lib = L.load()
@@ -70,27 +81,50 @@ def compute_rotation_curve(positions: torch.Tensor, velocities: torch.Tensor, nu
 
 
 def compute_galaxy_radius(positions: torch.Tensor, percentile: float = 90) -> float:
-    """Radius containing `percentile` % of the stars (reference metrics.py:81-95)."""
-    r = torch.sqrt((positions ** 2).sum(dim=-1))
-    k = int(len(r) * percentile / 100)
-    return torch.sort(r)[0][min(k, len(r) - 1)].item()
+    """Radius containing `percentile` % of the stars (reference metrics.py:81-95): the element of rank
+    min(int(N·p/100), N−1) of the sorted radii, selected without sorting (nb_radius_kth)."""
+    pos = _rows(positions)
+    n, dim = pos.shape
+    k = min(int(n * percentile / 100), n - 1)
+    lib = L.load()
+    out = torch.empty(1, dtype=pos.dtype, device=pos.device)
+    ws = torch.empty(lib.nb_metrics_workspace_bytes(), dtype=torch.uint8, device=pos.device)
+    with torch.cuda.device(pos.device):
+        L.check(lib.nb_radius_kth(L.ptr(pos), n, dim, L.dtype_code(pos), k, L.ptr(out), L.ptr(ws), ws.numel(),
+                                  L.stream_ptr(pos.device)), "nb_radius_kth")
+    return out.item()
 
 
 def compute_bound_fraction(positions: torch.Tensor, velocities: torch.Tensor, masses: torch.Tensor,
                            G: float = 0.001) -> float:
-    """Fraction of stars slower than the local escape speed (reference metrics.py:98-145)."""
-    com = (positions * masses.unsqueeze(-1)).sum(dim=0) / masses.sum()
-    r = torch.sqrt(((positions - com) ** 2).sum(dim=-1))
-    order = torch.argsort(r)
-    enclosed = torch.cumsum(masses[order], dim=0)[torch.argsort(order)]
-    v_esc = torch.sqrt(2 * G * enclosed / r.clamp(min=0.1))
+    """Fraction of stars slower than the escape speed of the mass enclosed by their radius about the centre of mass
+    (reference metrics.py:98-145).  Rank-ordered cumulative mass: device-side torch sort + cumsum (not yet a kernel)."""
+    total = masses.sum()
+    centre = (positions * masses.unsqueeze(-1)).sum(dim=0) / total
+    dist = torch.sqrt(((positions - centre) ** 2).sum(dim=-1))
+    by_radius = torch.argsort(dist)
+    enclosed = torch.cumsum(masses[by_radius], dim=0)[torch.argsort(by_radius)]
+    escape = torch.sqrt(2 * G * enclosed / dist.clamp(min=0.1))
     speed = torch.sqrt((velocities ** 2).sum(dim=-1))
-    return (speed < v_esc).float().mean().item()
+    return (speed < escape).float().mean().item()
 
 
 def compute_velocity_dispersion(velocities: torch.Tensor) -> float:
-    """Unbiased standard deviation of |v| (reference metrics.py:148-156)."""
-    return torch.sqrt((velocities ** 2).sum(dim=-1)).std().item()
+    """Unbiased standard deviation of |v| (reference metrics.py:148-156) from Σ|v| and Σ|v|² reduced in fp64."""
+    vel = _rows(velocities)
+    n, dim = vel.shape
+    lib = L.load()
+    out = torch.empty(2, dtype=torch.float64, device=vel.device)
+    ws = torch.empty(lib.nb_metrics_workspace_bytes(), dtype=torch.uint8, device=vel.device)
+    with torch.cuda.device(vel.device):
+        L.check(lib.nb_speed_moments(L.ptr(vel), n, dim, L.dtype_code(vel), L.ptr(out), L.ptr(ws), ws.numel(),
+                                     L.stream_ptr(vel.device)), "nb_speed_moments")
+    s1, s2 = out.tolist()
+    if n < 2:
+        return float("nan")                                        # torch.std of one element
+    var = max(s2 - s1 * s1 / n, 0.0) / (n - 1)
+    std = math.sqrt(var)
+    return float(np.float32(std)) if vel.dtype == torch.float32 else std
 
 
 def collect_metrics(simulation, tick: int, metrics: SimulationMetrics):
