@@ -110,7 +110,8 @@ int64_t nb_max_dist_workspace_bytes(int64_t n_src);
 int nb_max_dist_sq(const void* packed_src, int64_t n_src, int dim, int dtype, double eps_sq, int64_t* scalars,
                    void* workspace, int64_t workspace_bytes, void* stream);
 
-/* Bytes of the level table for `levels` grid levels. */
+/* Bytes of the level table for `levels` grid levels (header + one 16-byte record per level + the
+ * fast-lookup record). */
 int64_t nb_level_table_bytes(int levels);
 /* quantization.py:106-127 collapsed to a table: for each level k the snapped value u_k, the force
  * factor rn(rn(1/u_k^1.5)*G) (simulation.py:97-101) and the exact d² threshold at which
@@ -119,6 +120,14 @@ int64_t nb_level_table_bytes(int levels);
  * the tensor; hi comes from scalars[NB_SLOT_MAX_D2]. */
 int nb_build_level_table(const int64_t* scalars, int dtype, double eps_sq, double min_dist_sq, double G,
                          int levels, void* table, void* stream);
+
+/* Test hook for the fast level lookup nb_accel uses when levels <= 256 (csrc/lut.cuh): pushes EVERY float t
+ * in [max(eps², min_dist_sq), max d²] through (a) quantization.py:106-120 evaluated op by op, (b) the fast lookup,
+ * (c) its slow path, on the table nb_build_level_table wrote for the same scalars.  counters (uint64[4], device,
+ * zeroed by the caller) += { floats tested, floats the fast lookup hands to the slow path ("doubt"),
+ * fast-lookup levels != reference outside doubt, slow-path levels != reference }.  The last two must be 0. */
+int nb_lut_selfcheck(const int64_t* scalars, double eps_sq, double min_dist_sq, int levels, const void* level_table,
+                     uint64_t* counters, void* stream);
 
 /* acc_out[i,:] = Σ_j f(q(d²_ij))·m_j·(x_j − x_i)  for targets pos_tgt[0:n_tgt] against all n_src
  * packed sources (self pairs contribute exactly 0, as `* (1 - eye)` at simulation.py:108).

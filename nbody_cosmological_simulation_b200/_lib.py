@@ -13,7 +13,7 @@ from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTE
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnbody_b200.so")
+LIB_PATH = os.environ.get("NB_B200_LIB") or os.path.join(_HERE, "libnbody_b200.so")   # override: developer tuning builds only
 
 # dtype / mode / phase codes (include/nbody_b200.h)
 NB_F32, NB_F64 = 0, 1
@@ -41,6 +41,7 @@ PROTOTYPES = {
     "nb_max_dist_sq": (c_int, [_P, c_int64, c_int, c_int, c_double, _P, _P, c_int64, _P]),
     "nb_level_table_bytes": (c_int64, [c_int]),
     "nb_build_level_table": (c_int, [_P, c_int, c_double, c_double, c_double, c_int, _P, _P]),
+    "nb_lut_selfcheck": (c_int, [_P, c_double, c_double, c_int, _P, _P, _P]),
     "nb_accel": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_double, c_double, _P, c_int, c_int, c_double,
                          _P, _P, _P, c_int64, _P]),
     "nb_snap_accelerations": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),

@@ -12,10 +12,24 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include "stream.cuh"
+#include "lut.cuh"
 
 namespace nb {
 
-enum QMode { Q_F32 = 0, Q_F16 = 1, Q_BF16 = 2, Q_LUT = 3, Q_F64 = 4 };
+// tuning knobs of the fast-lookup kernel (tools/tune_lutf.sh builds variants)
+#ifndef NB_LUTF_MINB
+#define NB_LUTF_MINB 2
+#endif
+#ifndef NB_LUTF_UNROLL
+#define NB_LUTF_UNROLL 4
+#endif
+#ifndef NB_LUTF_IPT
+#define NB_LUTF_IPT 2
+#endif
+#ifndef NB_LUTF_THREADS
+#define NB_LUTF_THREADS 256
+#endif
+enum QMode { Q_F32 = 0, Q_F16 = 1, Q_BF16 = 2, Q_LUT = 3, Q_F64 = 4, Q_LUTF = 5 };   // Q_LUTF: fast level lookup (lut.cuh), L <= 256
 
 struct AccelArgs {
     const char* src;          // packed sources
@@ -52,6 +66,15 @@ struct ForceF32 {
     float neg_zero;
     const float4* lut;                     // shared-memory copy of the level table (Q_LUT)
     float lo2, scale, min_val;
+    // Q_LUTF (lut.cuh): lane-replicated factor table g[k][lane] (an LDS.32 at k·128 + lane·4 never bank-conflicts
+    // and moves 4× fewer shared-memory wavefronts than the 16-byte entries of Q_LUT), thresholds for the slow path
+    uint32_t lutg_lane;                    // shared-window address of g[0][lane]
+    const float* thr_smem;                 // T_j, j = 0..P
+    LutFast lf;
+    float2 scale2, cm2;
+    uint32_t kmask;                        // (P-1) << kLutFb: the level bits of W
+    int n_levels;
+    bool clamp_lo;                         // eps² < min_val: d² must be clamped from below (quantization.py:106)
 
     __device__ __forceinline__ void init(const AccelArgs& a, const float4* lut_smem) {
         const float* pos = reinterpret_cast<const float*>(a.pos_tgt);
@@ -77,12 +100,73 @@ struct ForceF32 {
             scale = h.y; min_val = h.z;
             lo2 = fmaf(-h.x, h.y, -0.5f + 1.0f / 64.0f);     // additive constant of the level estimate (see lut_factor)
         }
+        if (QMODE == Q_LUTF) {
+            const float4* tab = reinterpret_cast<const float4*>(a.table);
+            lf = lut_fast_load(tab, a.levels);
+            min_val = tab[0].z;
+            clamp_lo = e < min_val;
+            scale2 = make_float2(lf.scale, lf.scale);
+            cm2 = make_float2(lf.cm, lf.cm);
+            kmask = (uint32_t)(lf.p - 1) << kLutFb;
+            n_levels = a.levels;
+            lutg_lane = smem_u32(lut_smem) + 4u * (threadIdx.x & 31);
+            thr_smem = reinterpret_cast<const float*>(lut_smem) + 32 * lf.p;
+        }
+    }
+
+    // Q_LUTF: force factors of a source pair against one target.  Per scalar: MUFU.LG2, half an FFMA2, LOP3 + LEA.HI
+    // (address), LDS.32, LOP3 (doubt predicate).
+    __device__ __forceinline__ float2 lutf_lookup(float2 t, bool& doubt) const {
+        const float2 w = fma2(make_float2(lg2_approx(t.x), lg2_approx(t.y)), scale2, cm2);
+        const uint32_t wx = __float_as_uint(w.x), wy = __float_as_uint(w.y);
+        doubt = doubt || ((wx & lf.zmask) == 0u) || ((wy & lf.zmask) == 0u);
+        float2 g;
+        // address = &g[0][lane] + k·128 in the 32-bit shared window: LOP3 (mask the level bits) + LEA.HI (shift, add)
+        g.x = lds_f32(lutg_lane + ((wx & kmask) >> (kLutFb - 7)));
+        g.y = lds_f32(lutg_lane + ((wy & kmask) >> (kLutFb - 7)));
+        return g;
+    }
+    // Exact factor of one scalar pair (slow path): FULL = the factor itself, else the correction g_exact − g_fast that
+    // turns the fast path's contribution into the exact one (0 unless the pair is in doubt AND its level differs).
+    // t = d² in the reference's op order (defines the level), tf = the fused d² the main loop looked up
+    template <bool FULL>
+    __device__ __forceinline__ float lutf_exact(float t, float tf) const {
+        const uint32_t w = lut_wbits(tf, lf.scale, lf.cm);
+        const int k = lut_exact_level(t, w, lf, n_levels, thr_smem);
+        const float ge = lds_f32(lutg_lane + (uint32_t)(k * 128));
+        if (FULL) return ge;
+        const float gf = lds_f32(lutg_lane + ((w & kmask) >> (kLutFb - 7)));
+        return ge - gf;
+    }
+    template <bool FULL, bool CLAMP>
+    __device__ __noinline__ void lutf_redo(const unsigned char* s, int p) {
+        const float4 a = reinterpret_cast<const float4*>(s)[p];
+        const float2 xs = make_float2(a.x, a.y), ys = make_float2(a.z, a.w);
+        float2 zs = make_float2(0.f, 0.f), ms;
+        if (DIM == 3) { const float4 b = reinterpret_cast<const float4*>(s + kChunkABytes)[p]; zs = make_float2(b.x, b.y); ms = make_float2(b.z, b.w); }
+        else ms = reinterpret_cast<const float2*>(s + kChunkABytes)[p];
+#pragma unroll
+        for (int t = 0; t < IPT; ++t) {
+            const float2 dx = add2(xs, nx[t]), dy = add2(ys, ny[t]);
+            float2 dz = make_float2(0.f, 0.f);
+            if (DIM == 3) dz = add2(zs, nz[t]);
+            float2 tq = dist_sq<false>(dx, dy, dz), tf = dist_sq<true>(dx, dy, dz);
+            if (CLAMP) {
+                tq = make_float2(fmaxf(tq.x, min_val), fmaxf(tq.y, min_val));
+                tf = make_float2(fmaxf(tf.x, min_val), fmaxf(tf.y, min_val));
+            }
+            const float2 w = mul2(make_float2(lutf_exact<FULL>(tq.x, tf.x), lutf_exact<FULL>(tq.y, tf.y)), ms);
+            ax[t] = fma2(w, dx, ax[t]);
+            ay[t] = fma2(w, dy, ay[t]);
+            if (DIM == 3) az[t] = fma2(w, dz, az[t]);
+        }
     }
 
     // d² for a source pair: fused (fp32 mode, tolerance 1e-5) or the reference's exact rounding
     // sequence (modes whose next step is a snap: fp16/bf16 round trip, log-grid index).
+    template <bool FUSED = (QMODE == Q_F32)>
     __device__ __forceinline__ float2 dist_sq(float2 dx, float2 dy, float2 dz) const {
-        if (QMODE == Q_F32) {
+        if (FUSED) {
             float2 d2 = fma2(dx, dx, eps2);
             d2 = fma2(dy, dy, d2);
             if (DIM == 3) d2 = fma2(dz, dz, d2);
@@ -114,7 +198,69 @@ struct ForceF32 {
     float levels_m1_f;
     int lut_stride;
 
-    __device__ __forceinline__ void chunk(const unsigned char* s, int64_t) {
+    __device__ __forceinline__ void chunk(const unsigned char* s, int64_t c) {
+        if (QMODE == Q_LUTF) {
+            if (clamp_lo) chunk_lutf<true>(s); else chunk_lutf<false>(s);
+            return;
+        }
+        chunk_direct(s, c);
+    }
+
+    // Main loop without a branch: every iteration (one source pair x IPT targets) takes the fast lookup; an iteration
+    // with a d² in doubt pushes its index into a 4-entry queue held in ONE register (predicated LEA + IADD).  The queue
+    // is drained after the chunk, adding (g_exact − g_fast)·m·d for the queued iterations; more than 4 doubtful
+    // iterations in a chunk (only tables whose levels are denser than floats) redo the whole chunk on the slow path.
+    template <bool CLAMP>
+    __device__ __forceinline__ void chunk_lutf(const unsigned char* s) {
+        const float4* A = reinterpret_cast<const float4*>(s);
+        const float4* B4 = reinterpret_cast<const float4*>(s + kChunkABytes);
+        const float2* B2 = reinterpret_cast<const float2*>(s + kChunkABytes);
+        uint32_t queue = 0, queued = 0;
+#pragma unroll UNROLL
+        for (int p = 0; p < kChunkUnits; ++p) {
+            const float4 a = A[p];
+            const float2 xs = make_float2(a.x, a.y), ys = make_float2(a.z, a.w);
+            float2 zs = make_float2(0.f, 0.f), ms;
+            if (DIM == 3) { const float4 b = B4[p]; zs = make_float2(b.x, b.y); ms = make_float2(b.z, b.w); }
+            else ms = B2[p];
+            bool doubt = false;
+#pragma unroll
+            for (int t = 0; t < IPT; ++t) {
+                const float2 dx = add2(xs, nx[t]), dy = add2(ys, ny[t]);
+                float2 dz = make_float2(0.f, 0.f);
+                if (DIM == 3) dz = add2(zs, nz[t]);
+                float2 tq = dist_sq<true>(dx, dy, dz);   // fused d²: < 7 ulp from the exact-order value, inside the lookup margin (lut.cuh)
+                if (CLAMP) tq = make_float2(fmaxf(tq.x, min_val), fmaxf(tq.y, min_val));
+                const float2 w = mul2(lutf_lookup(tq, doubt), ms);
+                ax[t] = fma2(w, dx, ax[t]);
+                ay[t] = fma2(w, dy, ay[t]);
+                if (DIM == 3) az[t] = fma2(w, dz, az[t]);
+            }
+            if (doubt) { queue = (queue << 8) + (uint32_t)p; ++queued; }
+        }
+        if (queued) {
+            if (queued > 4u) {
+#pragma unroll
+                for (int t = 0; t < IPT; ++t) ax[t] = ay[t] = az[t] = make_float2(0.f, 0.f);
+                for (int p = 0; p < kChunkUnits; ++p) lutf_redo<true, CLAMP>(s, p);
+            } else {
+                for (; queued; --queued, queue >>= 8) lutf_redo<false, CLAMP>(s, (int)(queue & 0xffu));
+            }
+        }
+        flush();
+    }
+
+    __device__ __forceinline__ void flush() {
+        // flush the chunk-local fp32 sums into the fp64 accumulators
+#pragma unroll
+        for (int t = 0; t < IPT; ++t) {
+            sx[t] += (double)(ax[t].x + ax[t].y); ax[t] = make_float2(0.f, 0.f);
+            sy[t] += (double)(ay[t].x + ay[t].y); ay[t] = make_float2(0.f, 0.f);
+            if (DIM == 3) { sz[t] += (double)(az[t].x + az[t].y); az[t] = make_float2(0.f, 0.f); }
+        }
+    }
+
+    __device__ __forceinline__ void chunk_direct(const unsigned char* s, int64_t) {
         const float4* A = reinterpret_cast<const float4*>(s);
         const float4* B4 = reinterpret_cast<const float4*>(s + kChunkABytes);
         const float2* B2 = reinterpret_cast<const float2*>(s + kChunkABytes);
@@ -156,13 +302,7 @@ struct ForceF32 {
                 if (DIM == 3) az[t] = fma2(w, dz, az[t]);
             }
         }
-        // flush the chunk-local fp32 sums into the fp64 accumulators
-#pragma unroll
-        for (int t = 0; t < IPT; ++t) {
-            sx[t] += (double)(ax[t].x + ax[t].y); ax[t] = make_float2(0.f, 0.f);
-            sy[t] += (double)(ay[t].x + ay[t].y); ay[t] = make_float2(0.f, 0.f);
-            if (DIM == 3) { sz[t] += (double)(az[t].x + az[t].y); az[t] = make_float2(0.f, 0.f); }
-        }
+        flush();
     }
 
     __device__ __forceinline__ void store(const AccelArgs& a) const {
@@ -333,12 +473,13 @@ struct ForceMixed {       // fp32 sources/targets, FLOAT64 mode
 // ======================================================================================================
 constexpr int kMaxLevelsSmem = 4096;      // level table entries staged in shared memory (64 KB + header)
 
-template <class Consumer, bool USE_LUT>
-__global__ void __launch_bounds__(Consumer::THREADS + 32) accel_kernel(const AccelArgs a) {
+// LUTKIND: 0 = no level table, 1 = 16-byte entries replicated per bank group (Q_LUT), 2 = fast lookup (Q_LUTF)
+template <class Consumer, int LUTKIND>
+__global__ void __launch_bounds__(Consumer::THREADS + 32, LUTKIND == 2 ? NB_LUTF_MINB : 1) accel_kernel(const AccelArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const bool is_consumer = threadIdx.x < Consumer::THREADS;
     const float4* lut_smem = nullptr;
-    if (USE_LUT) {
+    if (LUTKIND == 1) {
         // the level table sits behind the streaming stages
         float4* dst = reinterpret_cast<float4*>(smem + stream_smem_bytes(Consumer::DIM));
         const float4* srcT = reinterpret_cast<const float4*>(a.table);
@@ -347,9 +488,23 @@ __global__ void __launch_bounds__(Consumer::THREADS + 32) accel_kernel(const Acc
         lut_smem = dst;
         __syncthreads();
     }
+    if (LUTKIND == 2) {
+        // g[k][lane] for k < P (0 beyond the last level), then T_j for j = 0..P (lut.cuh)
+        float* dst = reinterpret_cast<float*>(smem + stream_smem_bytes(Consumer::DIM));
+        const float4* srcT = reinterpret_cast<const float4*>(a.table);
+        const int P = lut_pow2ceil(a.levels);
+        for (int e = threadIdx.x; e < P * 32; e += blockDim.x) {
+            const int k = e >> 5;
+            dst[e] = k < a.levels ? srcT[1 + k].y : 0.f;
+        }
+        for (int j = threadIdx.x; j <= P; j += blockDim.x)
+            dst[P * 32 + j] = j == 0 ? 0.f : (j <= a.levels ? srcT[j].x : __int_as_float(0x7f800000));
+        lut_smem = reinterpret_cast<const float4*>(dst);
+        __syncthreads();
+    }
     Consumer cons;
     if (is_consumer) cons.init(a, lut_smem);
-    if constexpr (USE_LUT) cons.levels_m1_f = (float)(a.levels - 1);
+    if constexpr (LUTKIND == 1) cons.levels_m1_f = (float)(a.levels - 1);
     const int64_t c0 = (int64_t)blockIdx.y * a.chunks_per_split;
     const int64_t c1 = min(a.n_chunks, c0 + (int64_t)a.chunks_per_split);
     stream_sources(a.src, c0, c1, cons);
@@ -388,7 +543,7 @@ constexpr int kForceThreads = 256;
 constexpr int kForceIPT = 2;
 constexpr int kTargetsPerBlock = kForceThreads * kForceIPT;
 
-template <class Consumer, bool USE_LUT>
+template <class Consumer, int LUTKIND>
 int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, int* splits_out) {
     AccelArgs a = a0;
     const int64_t per_split = a.n_tgt * Consumer::DIM * (int64_t)sizeof(double);
@@ -397,12 +552,16 @@ int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, 
     const int cap = max_splits_for(a.n_tgt, Consumer::DIM);
     if (max_by_ws > cap) max_by_ws = cap;
     int smem = stream_smem_bytes(Consumer::DIM);
-    if (USE_LUT) {
+    if (LUTKIND == 1) {
         a.lut_rep = 8;                                        // as many copies as fit in 32 KB
         while (a.lut_rep > 1 && a.levels * a.lut_rep * 16 > 32 * 1024) a.lut_rep >>= 1;
         smem += (a.levels * a.lut_rep + 1) * 16;
     }
-    auto kern = accel_kernel<Consumer, USE_LUT>;
+    if (LUTKIND == 2) {
+        const int P = lut_pow2ceil(a.levels);
+        smem += P * 128 + (P + 1 + 3) / 4 * 16;
+    }
+    auto kern = accel_kernel<Consumer, LUTKIND>;
     int ctas_per_sm = 1;
     const int frc = kernel_occupancy((const void*)kern, Consumer::THREADS + 32, smem, &ctas_per_sm);
     if (frc != NB_OK) return frc;
@@ -455,22 +614,26 @@ extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_t
     // uniform-mass fast path exists for the two headline kernels (fp32 state/FLOAT32, fp64 state/FLOAT64)
     const bool uni = uniform_mass != 0 && ((dtype == NB_F32 && mode == NB_MODE_FLOAT32) || (dtype == NB_F64 && mode == NB_MODE_FLOAT64));
 #define NB_F32_CASE(D, Q, LUT) rc = launch_accel<ForceF32<D, Q, IPT, TH>, LUT>(a, workspace_bytes, st, &splits)
-#define NB_F64_CASE(D, Q) rc = launch_accel<ForceF64<D, Q, IPT, TH>, false>(a, workspace_bytes, st, &splits)
+#define NB_F64_CASE(D, Q) rc = launch_accel<ForceF64<D, Q, IPT, TH>, 0>(a, workspace_bytes, st, &splits)
     if (dtype == NB_F32) {
         if (mode == NB_MODE_FLOAT64) {
-            if (dim == 2) rc = launch_accel<ForceMixed<2, IPT, TH>, false>(a, workspace_bytes, st, &splits);
-            else rc = launch_accel<ForceMixed<3, IPT, TH>, false>(a, workspace_bytes, st, &splits);
+            if (dim == 2) rc = launch_accel<ForceMixed<2, IPT, TH>, 0>(a, workspace_bytes, st, &splits);
+            else rc = launch_accel<ForceMixed<3, IPT, TH>, 0>(a, workspace_bytes, st, &splits);
         } else if (mode == NB_MODE_FLOAT32 && uni) {
-            if (dim == 2) rc = launch_accel<ForceF32<2, Q_F32, IPT, TH, true>, false>(a, workspace_bytes, st, &splits);
-            else rc = launch_accel<ForceF32<3, Q_F32, IPT, TH, true>, false>(a, workspace_bytes, st, &splits);
-        } else if (mode == NB_MODE_FLOAT32) { if (dim == 2) NB_F32_CASE(2, Q_F32, false); else NB_F32_CASE(3, Q_F32, false); }
-        else if (mode == NB_MODE_FLOAT16) { if (dim == 2) NB_F32_CASE(2, Q_F16, false); else NB_F32_CASE(3, Q_F16, false); }
-        else if (mode == NB_MODE_BFLOAT16) { if (dim == 2) NB_F32_CASE(2, Q_BF16, false); else NB_F32_CASE(3, Q_BF16, false); }
-        else { if (dim == 2) NB_F32_CASE(2, Q_LUT, true); else NB_F32_CASE(3, Q_LUT, true); }
+            if (dim == 2) rc = launch_accel<ForceF32<2, Q_F32, IPT, TH, true>, 0>(a, workspace_bytes, st, &splits);
+            else rc = launch_accel<ForceF32<3, Q_F32, IPT, TH, true>, 0>(a, workspace_bytes, st, &splits);
+        } else if (mode == NB_MODE_FLOAT32) { if (dim == 2) NB_F32_CASE(2, Q_F32, 0); else NB_F32_CASE(3, Q_F32, 0); }
+        else if (mode == NB_MODE_FLOAT16) { if (dim == 2) NB_F32_CASE(2, Q_F16, 0); else NB_F32_CASE(3, Q_F16, 0); }
+        else if (mode == NB_MODE_BFLOAT16) { if (dim == 2) NB_F32_CASE(2, Q_BF16, 0); else NB_F32_CASE(3, Q_BF16, 0); }
+        else if (levels <= kLutFastMaxLevels) {
+            if (dim == 2) rc = launch_accel<ForceF32<2, Q_LUTF, NB_LUTF_IPT, NB_LUTF_THREADS, false, NB_LUTF_UNROLL>, 2>(a, workspace_bytes, st, &splits);
+            else rc = launch_accel<ForceF32<3, Q_LUTF, NB_LUTF_IPT, NB_LUTF_THREADS, false, NB_LUTF_UNROLL>, 2>(a, workspace_bytes, st, &splits);
+        }
+        else { if (dim == 2) NB_F32_CASE(2, Q_LUT, 1); else NB_F32_CASE(3, Q_LUT, 1); }
     } else {
         if (mode == NB_MODE_FLOAT64 && uni) {
-            if (dim == 2) rc = launch_accel<ForceF64<2, Q_F64, IPT, TH, true>, false>(a, workspace_bytes, st, &splits);
-            else rc = launch_accel<ForceF64<3, Q_F64, IPT, TH, true>, false>(a, workspace_bytes, st, &splits);
+            if (dim == 2) rc = launch_accel<ForceF64<2, Q_F64, IPT, TH, true>, 0>(a, workspace_bytes, st, &splits);
+            else rc = launch_accel<ForceF64<3, Q_F64, IPT, TH, true>, 0>(a, workspace_bytes, st, &splits);
         } else if (mode == NB_MODE_FLOAT64) { if (dim == 2) NB_F64_CASE(2, Q_F64); else NB_F64_CASE(3, Q_F64); }
         else if (mode == NB_MODE_FLOAT32) { if (dim == 2) NB_F64_CASE(2, Q_F32); else NB_F64_CASE(3, Q_F32); }
         else if (mode == NB_MODE_FLOAT16) { if (dim == 2) NB_F64_CASE(2, Q_F16); else NB_F64_CASE(3, Q_F16); }

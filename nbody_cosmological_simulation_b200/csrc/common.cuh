@@ -88,6 +88,12 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src_
                  : "memory");
 }
 
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));   // not volatile: read-only tables, free to schedule
+    return v;
+}
+
 // ---- packed fp32x2 math (sm_100 FFMA2 / FADD2 / FMUL2) ------------------------------------------------
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }

@@ -7,6 +7,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include "stream.cuh"
+#include "lut.cuh"
 
 namespace nb {
 
@@ -39,35 +40,51 @@ __device__ __forceinline__ T log_grid_value(T k, T lo, T span, T lm1, T min_val)
 }
 
 // ---- level table -------------------------------------------------------------------------------------
-struct LevelHeader { float lo2, scale, min_val, degenerate; };
+// Layout (float4 records): [0] header { lo2, scale, min_val, degenerate }, [1 + k] level k = { T_{k+1}, g_k, g_{k+1}, 0 },
+// [1 + L] fast-lookup record (lut.cuh).  Launched as ONE block when L <= kLutFastMaxLevels so that the margin of
+// the fast lookup can be reduced over all thresholds in the same launch.
+struct LevelGrid {
+    float t_lo, t_hi, lo, hi, span, lm1, lo2, scale;
+    bool degenerate;
+};
+
+__device__ __forceinline__ LevelGrid level_grid(const int64_t* __restrict__ scalars, float eps2, float min_val, int levels) {
+    LevelGrid g;
+    g.t_lo = fmaxf(eps2, min_val);                                             // the diagonal: smallest clamped d²
+    g.t_hi = fmaxf((float)double_from_key(scalars[NB_SLOT_MAX_D2]), min_val);
+    g.lo = q_log(g.t_lo); g.hi = q_log(g.t_hi);
+    g.span = q_sub(g.hi, g.lo);
+    g.lm1 = (float)(levels - 1);
+    g.degenerate = g.span < 1e-10f;                                            // quantization.py:115
+    g.lo2 = log2f(g.t_lo);
+    g.scale = g.degenerate ? 0.f : g.lm1 / (log2f(g.t_hi) - g.lo2);
+    return g;
+}
 
 __global__ void __launch_bounds__(256) build_level_table_kernel(const int64_t* __restrict__ scalars, float eps2, float min_val,
                                                                 float G, int levels, float4* __restrict__ table) {
-    const float t_lo = fmaxf(eps2, min_val);                                   // the diagonal: smallest clamped d²
-    const float t_hi = fmaxf((float)double_from_key(scalars[NB_SLOT_MAX_D2]), min_val);
-    const float lo = q_log(t_lo), hi = q_log(t_hi);
-    const float span = q_sub(hi, lo);
-    const float lm1 = (float)(levels - 1);
-    const bool degenerate = span < 1e-10f;                                     // quantization.py:115
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const float lo2 = log2f(t_lo), hi2 = log2f(t_hi);
-        LevelHeader h;
-        h.lo2 = lo2;
-        h.scale = degenerate ? 0.f : lm1 / (hi2 - lo2);
-        h.min_val = min_val;
-        h.degenerate = degenerate ? 1.f : 0.f;
-        table[0] = make_float4(h.lo2, h.scale, h.min_val, h.degenerate);
-    }
+    __shared__ int red[32];
+    const LevelGrid gr = level_grid(scalars, eps2, min_val, levels);
+    const float lo = gr.lo, span = gr.span, lm1 = gr.lm1;
+    const bool degenerate = gr.degenerate;
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        table[0] = make_float4(gr.lo2, gr.scale, min_val, degenerate ? 1.f : 0.f);
+    // fast lookup (lut.cuh): W = fma(lg2 t, scale, cm0) lands on a 2^-fb grid in [2P, 4P)
+    const bool fast = levels <= kLutFastMaxLevels;                             // then gridDim.x == 1
+    const int P = lut_pow2ceil(levels), fb = kLutFb;
+    const float M = 3.0f * (float)kLutGridP;
+    const float cm0 = q_add(fmaf(-gr.lo2, gr.scale, 0.5f), M);
+    int need = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < levels; k += gridDim.x * blockDim.x) {
         auto factor = [&](int kk) -> float {
             // u_k -> G / u_k^1.5 as torch evaluates it: pow, reciprocal, mul by G   (simulation.py:97-101)
-            const float u = degenerate ? t_hi : log_grid_value((float)kk, lo, span, lm1, min_val);
+            const float u = degenerate ? gr.t_hi : log_grid_value((float)kk, lo, span, lm1, min_val);
             return q_mul(__frcp_rn(powf(u, 1.5f)), G);
         };
         float thr = __int_as_float(0x7f800000);                                // T_L = +inf
         if (!degenerate && k + 1 < levels) {
             // smallest float t in [t_lo, t_hi] whose level index is >= k+1 (index is monotone in t)
-            unsigned lo_b = __float_as_uint(t_lo), hi_b = __float_as_uint(t_hi);
+            unsigned lo_b = __float_as_uint(gr.t_lo), hi_b = __float_as_uint(gr.t_hi);
             const float target = (float)(k + 1);
             while (hi_b - lo_b > 1u) {
                 const unsigned mid = lo_b + ((hi_b - lo_b) >> 1);
@@ -75,8 +92,76 @@ __global__ void __launch_bounds__(256) build_level_table_kernel(const int64_t* _
                 if (idx >= target) hi_b = mid; else lo_b = mid;
             }
             thr = __uint_as_float(hi_b);
+            if (fast) {
+                // distance of the fast lookup's fixed-point position from the ideal (k+1)·2^fb at the threshold and
+                // just below it: W(T_j) must not be below the boundary by more than the margin, W(prev T_j) not above
+                // — evaluated kLutD2Slack floats further out, because the force kernel feeds the lookup the FUSED d²
+                // (2-3 roundings) while the level is defined on the reference's op-by-op d² (4-6 roundings)
+                const int ideal = (k + 1) << fb;
+                const int v_at = (int)(lut_wbits(__uint_as_float(hi_b - kLutD2Slack), gr.scale, cm0) - __float_as_uint(M));
+                const int v_below = (int)(lut_wbits(__uint_as_float(hi_b - 1u + kLutD2Slack), gr.scale, cm0) - __float_as_uint(M));
+                need = max(need, max(ideal - v_at, v_below - ideal + 1));
+            }
         }
         table[1 + k] = make_float4(thr, factor(k), k + 1 < levels ? factor(k + 1) : 0.f, 0.f);
+    }
+    if (fast) {
+        need = block_reduce(need, OpMax(), 0, red);
+        if (threadIdx.x == 0) {
+            const long long mg = (long long)need + 2;                          // + slack for lg2.approx non-monotonicity
+            long long mgp = 2;
+            while (mgp < mg) mgp <<= 1;
+            const long long span_fb = 1ll << fb;
+            const uint32_t zmask = 2 * mgp >= span_fb ? 0u : (uint32_t)((span_fb - 1) & ~(2 * mgp - 1));
+            const int single_ok = mgp <= (span_fb >> 2) ? 1 : 0;
+            const float cm = zmask ? q_add(cm0, (float)mgp * exp2f((float)-fb)) : cm0;
+            table[1 + levels] = make_float4(cm, __uint_as_float(zmask), __int_as_float(fb | (single_ok << 8)), __int_as_float(P));
+        }
+    } else if (threadIdx.x == 0 && blockIdx.x == 0) {
+        table[1 + levels] = make_float4(cm0, 0.f, __int_as_float(fb), __int_as_float(P));
+    }
+}
+
+// Exhaustive proof of the fast lookup for one table: every float t in [t_lo, t_hi] is pushed through (a) the
+// reference's op sequence round((log t - lo)/(hi - lo)·(L-1)), (b) the fast lookup, (c) the slow path.
+// counters: [0] floats tested, [1] floats in doubt, [2] fast-path mismatches outside doubt, [3] slow-path mismatches.
+struct TableThresholds {
+    const float4* table; int levels;
+    __device__ __forceinline__ float operator[](int j) const {
+        return j <= 0 ? 0.f : (j <= levels ? table[j].x : __int_as_float(0x7f800000));
+    }
+};
+
+__global__ void __launch_bounds__(256) lut_selfcheck_kernel(const int64_t* __restrict__ scalars, float eps2, float min_val, int levels,
+                                                            const float4* __restrict__ table, unsigned long long* __restrict__ counters) {
+    __shared__ unsigned long long red[32];
+    const LevelGrid gr = level_grid(scalars, eps2, min_val, levels);
+    const LutFast f = lut_fast_load(table, levels);
+    const TableThresholds thr{table, levels};
+    const uint32_t b0 = __float_as_uint(gr.t_lo), b1 = __float_as_uint(gr.t_hi);
+    unsigned long long tested = 0, doubt = 0, bad_fast = 0, bad_slow = 0;
+    if (!gr.degenerate) {
+        for (uint64_t b = (uint64_t)b0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b <= b1; b += (uint64_t)gridDim.x * blockDim.x) {
+            const float t = __uint_as_float((uint32_t)b);
+            const int k_ref = (int)q_rint(log_grid_normalized(t, gr.lo, gr.span, gr.lm1));
+            ++tested;
+            doubt += (lut_wbits(t, f.scale, f.cm) & f.zmask) == 0u;
+            // the lookup sees a d² that may sit up to kLutD2Slack floats away from the exact-order d² = t
+            for (int o = -(int)kLutD2Slack; o <= (int)kLutD2Slack; ++o) {
+                const uint32_t wf = lut_wbits(__uint_as_float((uint32_t)((int64_t)b + o)), f.scale, f.cm);
+                const int k_fast = (int)((wf >> f.fb) & (uint32_t)(f.p - 1));
+                bad_fast += ((wf & f.zmask) != 0u && k_fast != k_ref);
+                bad_slow += (lut_exact_level(t, wf, f, levels, thr) != k_ref);
+            }
+        }
+    }
+    tested = block_reduce(tested, OpAdd(), 0ull, red);
+    doubt = block_reduce(doubt, OpAdd(), 0ull, red);
+    bad_fast = block_reduce(bad_fast, OpAdd(), 0ull, red);
+    bad_slow = block_reduce(bad_slow, OpAdd(), 0ull, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(counters + 0, tested); atomicAdd(counters + 1, doubt);
+        atomicAdd(counters + 2, bad_fast); atomicAdd(counters + 3, bad_slow);
     }
 }
 
@@ -183,15 +268,25 @@ extern "C" int nb_reset_scalars(int64_t* scalars, void* stream) {
     return NB_OK;
 }
 
-extern "C" int64_t nb_level_table_bytes(int levels) { return levels < 2 ? 0 : (int64_t)(levels + 1) * 16; }
+extern "C" int64_t nb_level_table_bytes(int levels) { return levels < 2 ? 0 : (int64_t)(levels + 2) * 16; }
 
 extern "C" int nb_build_level_table(const int64_t* scalars, int dtype, double eps_sq, double min_dist_sq, double G, int levels,
                                     void* table, void* stream) {
     if (!scalars || !table || levels < 2) return NB_ERR_INVALID_ARGUMENT;
     if (dtype != NB_F32) return NB_ERR_UNSUPPORTED;
-    const int blocks = (levels + 255) / 256;
+    const int blocks = levels <= kLutFastMaxLevels ? 1 : (levels + 255) / 256;
     build_level_table_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(scalars, (float)eps_sq, (float)min_dist_sq, (float)G, levels,
                                                                         (float4*)table);
+    NB_CUDA_LAUNCH_CHECK();
+    return NB_OK;
+}
+
+extern "C" int nb_lut_selfcheck(const int64_t* scalars, double eps_sq, double min_dist_sq, int levels, const void* table,
+                                uint64_t* counters, void* stream) {
+    if (!scalars || !table || !counters || levels < 2) return NB_ERR_INVALID_ARGUMENT;
+    if (levels > kLutFastMaxLevels) return NB_ERR_UNSUPPORTED;
+    lut_selfcheck_kernel<<<kNumSMsB200 * 8, 256, 0, (cudaStream_t)stream>>>(scalars, (float)eps_sq, (float)min_dist_sq, levels,
+                                                                            (const float4*)table, (unsigned long long*)counters);
     NB_CUDA_LAUNCH_CHECK();
     return NB_OK;
 }

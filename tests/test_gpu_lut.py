@@ -1,0 +1,44 @@
+"""The fast level lookup of the int-mode force kernel (csrc/lut.cuh) against quantization.py:106-120, EXHAUSTIVELY:
+every float between the smallest and the largest clamped d² of a table is pushed through the reference's op
+sequence, the fast lookup and its slow path on the device (nb_lut_selfcheck) — bit-exact level indices are the
+bar (BASELINE.json north_star: "quantized grid indices bit-exact given identical pre-snap values").
+Needs a B200: `-m gpu`."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = torch.device("cuda:0")
+
+
+def selfcheck(max_d2, eps_sq, levels, min_dist_sq=0.01, G=1e-3):
+    from nbody_cosmological_simulation_b200 import _lib as L
+    lib = L.load()
+    scalars = torch.zeros(8, dtype=torch.int64, device=DEV)
+    L.check(lib.nb_reset_scalars(L.ptr(scalars), L.stream_ptr(DEV)))
+    scalars[0] = lib.nb_key_from_double(float(max_d2))
+    table = torch.zeros(lib.nb_level_table_bytes(levels), dtype=torch.uint8, device=DEV)
+    L.check(lib.nb_build_level_table(L.ptr(scalars), 0, float(eps_sq), float(min_dist_sq), float(G), levels, L.ptr(table),
+                                     L.stream_ptr(DEV)))
+    counters = torch.zeros(4, dtype=torch.int64, device=DEV)
+    L.check(lib.nb_lut_selfcheck(L.ptr(scalars), float(eps_sq), float(min_dist_sq), levels, L.ptr(table), L.ptr(counters),
+                                 L.stream_ptr(DEV)))
+    torch.cuda.synchronize()
+    return [int(v) for v in counters.cpu()]
+
+
+@pytest.mark.parametrize("levels", [16, 256, 64, 2, 3, 100, 255])
+@pytest.mark.parametrize("max_d2,eps_sq", [(1600.0, 0.01), (412.7, 0.01), (3.0e4, 0.0025), (1.3e6, 1.0), (0.5, 1e-4)])
+def test_fast_lookup_is_exact_for_every_float_in_range(levels, max_d2, eps_sq):
+    tested, doubt, bad_fast, bad_slow = selfcheck(max_d2, eps_sq, levels)
+    assert tested > 1_000_000                     # 2^23 floats per octave
+    assert bad_fast == 0 and bad_slow == 0
+    assert doubt / tested < 0.02                  # the slow path stays rare (measured: ~5e-4 at L = 256)
+
+
+def test_fast_lookup_survives_grids_denser_than_floats():
+    # 256 levels squeezed between two nearly equal d² values: several levels per float step, so the margin blows up
+    # and every t must take the (binary-search) slow path — still exact.
+    eps_sq = 1.0
+    tested, doubt, bad_fast, bad_slow = selfcheck(1.0 + 3e-5, eps_sq, 256)
+    assert tested > 100 and bad_fast == 0 and bad_slow == 0

@@ -40,7 +40,7 @@ def test_host_only_helpers_need_no_gpu():
     assert lib.nb_chunk_bytes(3, 0) == 4096 and lib.nb_chunk_bytes(2, 0) == 3072
     assert lib.nb_num_chunks(1 << 20, 0) == 4096 and lib.nb_packed_bytes(1000, 3, 0) == 4 * 4096
     assert lib.nb_accel_workspace_bytes(1 << 20, 3) >= (1 << 20) * 3 * 8
-    assert lib.nb_level_table_bytes(16) == 17 * 16
+    assert lib.nb_level_table_bytes(16) == 18 * 16      # header + 16 levels + fast-lookup record
     vals = [-np.inf, -3.5, -0.0, 0.0, 1e-300, 2.5, np.inf]
     keys = [lib.nb_key_from_double(v) for v in vals]
     assert keys == sorted(keys)                                 # order-preserving keys

@@ -41,6 +41,9 @@ __global__ void __launch_bounds__(1024, 1) k_fp32(float* out, float seed, unsign
                 if (OP == 2) a[i] = __fadd_rn(a[i], c);
                 if (OP == 3) asm volatile("rsqrt.approx.f32 %0, %0;" : "+f"(a[i]));
                 if (OP == 4) a[i] = fmaxf(a[i], c) + 0.0f * b;     // FMNMX (alu pipe) — the add folds away
+                if (OP == 5) { float x = fabsf(a[i]); asm volatile("lg2.approx.ftz.f32 %0, %1;" : "=f"(a[i]) : "f"(x)); }   // MUFU.LG2 R, |R|
+                if (OP == 6) { float x = -fabsf(a[i]); asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(a[i]) : "f"(x)); }  // MUFU.EX2 R, -|R|
+                if (OP == 7) { float x = fabsf(a[i]); asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(a[i]) : "f"(x)); } // MUFU.RSQ R, |R|
             }
         }
     }
@@ -162,6 +165,9 @@ int main() {
     run("fmul",      [&] { k_fp32<1><<<blocks, threads>>>((float*)out, 1.0001f, dcyc); }, n, 1);
     run("fadd",      [&] { k_fp32<2><<<blocks, threads>>>((float*)out, 1.0001f, dcyc); }, n, 1);
     run("mufu_rsq",  [&] { k_fp32<3><<<blocks, threads>>>((float*)out, 1.0001f, dcyc); }, n, 1);
+    run("mufu_lg2",  [&] { k_fp32<5><<<blocks, threads>>>((float*)out, 1.0001f, dcyc); }, n, 1);
+    run("mufu_ex2",  [&] { k_fp32<6><<<blocks, threads>>>((float*)out, 1.0001f, dcyc); }, n, 1);
+    run("mufu_rsq_nochain", [&] { k_fp32<7><<<blocks, threads>>>((float*)out, 1.0001f, dcyc); }, n, 1);
     run("fmnmx",     [&] { k_fp32<4><<<blocks, threads>>>((float*)out, 1.0001f, dcyc); }, n, 1);
     run("ffma2",     [&] { k_fp32x2<0><<<blocks, threads>>>((float*)out, 1.0001f, dcyc); }, 2 * n, 2);
     run("fmul2",     [&] { k_fp32x2<1><<<blocks, threads>>>((float*)out, 1.0001f, dcyc); }, 2 * n, 1);

@@ -13,16 +13,16 @@ template <class Consumer>
 static void run(const char* name, const AccelArgs& a, int64_t ws_bytes, double n_inter) {
     int splits = 0;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    int rc = launch_accel<Consumer, false>(a, ws_bytes, 0, &splits);
+    int rc = launch_accel<Consumer, 0>(a, ws_bytes, 0, &splits);
     if (rc) { printf("%-34s launch failed rc=%d\n", name, rc); return; }
     cudaDeviceSynchronize();
     float best = 1e30f;
     for (int r = 0; r < 4; ++r) {
-        cudaEventRecord(e0); launch_accel<Consumer, false>(a, ws_bytes, 0, &splits); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventRecord(e0); launch_accel<Consumer, 0>(a, ws_bytes, 0, &splits); cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
-    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, accel_kernel<Consumer, false>);
-    int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, accel_kernel<Consumer, false>, Consumer::THREADS + 32, stream_smem_bytes(Consumer::DIM));
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, accel_kernel<Consumer, 0>);
+    int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, accel_kernel<Consumer, 0>, Consumer::THREADS + 32, stream_smem_bytes(Consumer::DIM));
     printf("%-34s regs %3d occ %d splits %2d  %8.3f ms  %6.3f T inter/s  %6.2f TFLOP/s@20\n", name, fa.numRegs, occ, splits, best,
            n_inter / (best * 1e-3) / 1e12, 20 * n_inter / (best * 1e-3) / 1e12);
 }
