@@ -22,6 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from . import overrides
 from .quantization import PrecisionMode, levels_for_mode
 
 _INT_FORCE_SNAP = {PrecisionMode.INT8_SIM: 256, PrecisionMode.INT4_SIM: 16}      # simulation.py:115
@@ -72,8 +73,13 @@ class GalaxySimulation:
         self._buffers: Optional[_DeviceBuffers] = None
         self._packed_key = None
 
-        # reference simulation.py:69 — one force evaluation at construction
-        self.accelerations = self._compute_accelerations()
+        # reference simulation.py:69 — one force evaluation at construction (through the hook; a recognised
+        # script override is evaluated natively, see _force_spec)
+        spec = self._force_spec()
+        if spec is not None and not self._is_stock(self, "_compute_accelerations"):
+            self.accelerations = GalaxySimulation._compute_accelerations(self)
+        else:
+            self.accelerations = self._compute_accelerations()
         self.tick = 0
 
     # ------------------------------------------------------------------------------------------
@@ -89,6 +95,32 @@ class GalaxySimulation:
     @staticmethod
     def _is_stock(obj, name: str) -> bool:
         return getattr(type(obj), name) is getattr(GalaxySimulation, name)
+
+    MAX_GRID_LEVELS = 4096                 # level tables up to this size fit the force kernel's shared memory
+
+    def _force_spec(self):
+        """(mode, d²-grid levels, min_dist_sq, force-snap levels) the native force kernel should run with, or None
+        when `_compute_accelerations` is user code that must run as written.  Stock hook: from `precision_mode`
+        (simulation.py:74-118).  Overridden hook: only the canonical script override (overrides.py), whose body is
+        the CUSTOM-mode arithmetic with its own `levels` / `min_val` and no force snap."""
+        if self._is_stock(self, "_compute_accelerations"):
+            mode = self.precision_mode
+            return mode, levels_for_mode(mode) or 0, 0.01, _INT_FORCE_SNAP.get(mode, 0)
+        spec = overrides.recognise(type(self), GalaxySimulation._compute_accelerations)
+        if spec is None:
+            return None
+        try:
+            x, m = self.positions, self.masses
+            if not (x.is_cuda and x.dtype == torch.float32 and m.dtype == torch.float32):
+                return None                # the override's arithmetic follows the tensors' dtype; only fp32 is native
+            if not spec.quantised(self):
+                return PrecisionMode.FLOAT32, 0, 0.01, 0
+            levels = spec.levels.value(self)
+        except (AttributeError, TypeError, ValueError):
+            return None
+        if not 2 <= levels <= self.MAX_GRID_LEVELS:
+            return None
+        return PrecisionMode.CUSTOM, levels, float(spec.min_val), 0
 
     def _state(self):
         """(x, v, m) as contiguous CUDA fp32/fp64 tensors; x and v share one dtype."""
@@ -120,14 +152,14 @@ class GalaxySimulation:
     # ------------------------------------------------------------------------------------------
     # force evaluation — reference simulation.py:74-118
     # ------------------------------------------------------------------------------------------
-    def _accelerations_raw(self, x: torch.Tensor, m: torch.Tensor, packed: torch.Tensor):
+    def _accelerations_raw(self, x: torch.Tensor, m: torch.Tensor, packed: torch.Tensor, spec=None):
         """Pre-snap accelerations of all stars and the force-snap level count (0 = none)."""
         lib, buf = L.load(), self._buf()
         n, dim = x.shape
         code = L.dtype_code(x)
-        mode = self.precision_mode
+        mode, levels, min_dist_sq, snap_levels = spec or self._force_spec() or \
+            (self.precision_mode, levels_for_mode(self.precision_mode) or 0, 0.01, _INT_FORCE_SNAP.get(self.precision_mode, 0))
         mode_code = L.MODE_CODES[mode.value]
-        levels = levels_for_mode(mode) or 0
         out_dtype = torch.float64 if (code == L.NB_F64 or mode == PrecisionMode.FLOAT64) else torch.float32
         acc = torch.empty((n, dim), dtype=out_dtype, device=x.device)
         ws_bytes = max(lib.nb_accel_workspace_bytes(n, dim), lib.nb_max_dist_workspace_bytes(n) if levels else 0)
@@ -142,13 +174,13 @@ class GalaxySimulation:
                 L.check(lib.nb_max_dist_sq(L.ptr(packed), n, dim, code, eps_sq, L.ptr(buf.scalars), L.ptr(ws), ws.numel(),
                                            st), "nb_max_dist_sq")
                 table = buf.bytes("level_table", lib.nb_level_table_bytes(levels))
-                L.check(lib.nb_build_level_table(L.ptr(buf.scalars), code, eps_sq, 0.01, float(self.G), levels,
+                L.check(lib.nb_build_level_table(L.ptr(buf.scalars), code, eps_sq, min_dist_sq, float(self.G), levels,
                                                  L.ptr(table), st), "nb_build_level_table")
             L.check(lib.nb_accel(L.ptr(packed), n, L.ptr(x), n, dim, code, mode_code, float(self.G), eps_sq,
                                  L.ptr(table), levels, int(uni), m0, L.ptr(acc), L.ptr(buf.scalars), L.ptr(ws),
                                  ws.numel(), st),
                     "nb_accel")
-        return acc, _INT_FORCE_SNAP.get(mode, 0)
+        return acc, snap_levels
 
     def _compute_accelerations(self) -> torch.Tensor:
         """Gravitational accelerations of all stars in the current precision mode (overridable hook)."""
@@ -193,18 +225,19 @@ class GalaxySimulation:
 
     def step(self):
         """One kick-drift-kick leapfrog tick (reference simulation.py:120-143)."""
-        stock_force = self._is_stock(self, "_compute_accelerations")
+        spec = self._force_spec()                  # None: the force hook is user code
+        stock_force = spec is not None
         if stock_force and not getattr(self, "_explicit_step", False):
             # one native call (kick-drift, force, closing kick) instead of four calls from Python; bit-identical to the
             # explicit sequence below, which stays for instrumentation (bench.py times the force launch with it)
-            self._run_fused(1)
+            self._run_fused(1, spec)
             return
         x, v, m, a = self._promoted_state(self.accelerations)
         if stock_force:
             x, v = self._kdk(L.KDK_KICK_DRIFT, x, v, a, m, emit_packed=True)
             self.positions, self.velocities = x, v
             packed = self._buf().bytes(f"packed{L.dtype_code(x)}", 0)
-            acc, snap_levels = self._accelerations_raw(x, m, packed)
+            acc, snap_levels = self._accelerations_raw(x, m, packed, spec)
             # second half kick; int modes snap the fresh accelerations inside the same kernel
             _, v = self._kdk(L.KDK_KICK, None, v, acc, m, snap_levels=snap_levels)
             self.accelerations, self.velocities = acc, v
@@ -223,7 +256,7 @@ class GalaxySimulation:
     # below this many particles a tick is launch-latency bound: replay it from a CUDA graph
     GRAPH_MAX_STARS = 65536
 
-    def _run_fused(self, ticks: int):
+    def _run_fused(self, ticks: int, spec=None):
         """`ticks` stock ticks in ONE native call (nb_run_ticks): the closing half kick of tick t is fused into the
         opening of tick t+1, the tick body is replayed from a CUDA graph for small systems, and the state is
         updated in place on private copies (tensors the caller still holds are never mutated)."""
@@ -231,15 +264,13 @@ class GalaxySimulation:
             return
         lib, buf = L.load(), self._buf()
         x, v, m, a = self._promoted_state(self.accelerations)
-        mode = self.precision_mode
+        mode, levels, min_dist_sq, snap_levels = spec or self._force_spec()
         # fresh output buffers: the first tick reads the current state and writes these, later ticks update them in
         # place — tensors the caller still holds are never mutated (the reference rebinds, never writes in place)
         x_in, v_in, a_in = x, v, a
         x, v, a = torch.empty_like(x_in), torch.empty_like(v_in), torch.empty_like(a_in)
         n, dim = x.shape
         code = L.dtype_code(x)
-        levels = levels_for_mode(mode) or 0
-        snap_levels = _INT_FORCE_SNAP.get(mode, 0)
         uni, m0 = L.uniform_mass(m) if mode in (PrecisionMode.FLOAT32, PrecisionMode.FLOAT64) else (False, 0.0)
         packed = buf.bytes(f"packed{code}", lib.nb_packed_bytes(n, dim, code))
         table = buf.bytes("level_table", lib.nb_level_table_bytes(levels)) if levels else None
@@ -249,7 +280,7 @@ class GalaxySimulation:
             L.check(lib.nb_run_ticks(L.ptr(x_in), L.ptr(v_in), L.ptr(a_in), L.ptr(x), L.ptr(v), L.ptr(a), L.ptr(m), n, dim,
                                      code, L.dtype_code(m),
                                      L.MODE_CODES[mode.value], levels, snap_levels, float(self.G), float(self.softening_sq),
-                                     0.01, float(self.dt), int(ticks), int(uni), m0, L.ptr(packed), L.ptr(table),
+                                     float(min_dist_sq), float(self.dt), int(ticks), int(uni), m0, L.ptr(packed), L.ptr(table),
                                      L.ptr(buf.scalars), L.ptr(ws), ws.numel(), int(n <= self.GRAPH_MAX_STARS),
                                      L.stream_ptr(x.device)), "nb_run_ticks")
         self._packed_key = self._packed_cache_key(x, m, packed)      # packed holds the records of the final positions
@@ -258,8 +289,8 @@ class GalaxySimulation:
 
     def run(self, num_ticks: int, callback: Callable = None, callback_interval: int = 100):
         """Run `num_ticks` ticks; `callback(sim, sim.tick)` every `callback_interval` (simulation.py:145-158)."""
-        stock = self._is_stock(self, "step") and self._is_stock(self, "_compute_accelerations")
-        if not stock:
+        spec = self._force_spec() if self._is_stock(self, "step") else None
+        if spec is None:
             for t in range(num_ticks):
                 self.step()
                 if callback and (t + 1) % callback_interval == 0:
@@ -272,7 +303,7 @@ class GalaxySimulation:
                 span = min(until_cb, num_ticks - done)
             else:
                 span = num_ticks - done
-            self._run_fused(span)
+            self._run_fused(span, spec)
             done += span
             if callback and done % callback_interval == 0:
                 callback(self, self.tick)
