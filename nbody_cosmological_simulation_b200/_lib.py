@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTER
 
 import torch
@@ -118,17 +119,20 @@ _uniform_cache = {}
 
 
 def uniform_mass(m: torch.Tensor):
-    """(is_uniform, value) for a mass tensor; one device->host read per distinct (tensor, version), then cached."""
+    """(is_uniform, value) for a mass tensor; one device->host read per distinct (tensor object, version), then
+    cached.  The entry holds a weak reference to the tensor: the caching allocator recycles addresses, so a key made
+    of data_ptr alone would serve a dead tensor's answer to a new tensor that landed on the same address."""
     key = (m.data_ptr(), m._version, m.numel(), m.dtype)
     hit = _uniform_cache.get(key)
-    if hit is None:
-        if len(_uniform_cache) > 64:
-            _uniform_cache.clear()
-        lo, hi = torch.aminmax(m)
-        lo, hi = lo.item(), hi.item()
-        hit = (lo == hi, float(lo))
-        _uniform_cache[key] = hit
-    return hit
+    if hit is not None and hit[0]() is m:
+        return hit[1]
+    if len(_uniform_cache) > 64:
+        _uniform_cache.clear()
+    lo, hi = torch.aminmax(m)
+    lo, hi = lo.item(), hi.item()
+    value = (lo == hi, float(lo))
+    _uniform_cache[key] = (weakref.ref(m), value)
+    return value
 
 
 def ptr(t):

@@ -145,6 +145,9 @@ struct ForceF32 {
         float2 zs = make_float2(0.f, 0.f), ms;
         if (DIM == 3) { const float4 b = reinterpret_cast<const float4*>(s + kChunkABytes)[p]; zs = make_float2(b.x, b.y); ms = make_float2(b.z, b.w); }
         else ms = reinterpret_cast<const float2*>(s + kChunkABytes)[p];
+        // massless records (the padding of the last chunk: 240 identical far-away points whose common W may well sit in
+        // the doubt zone and then overflow every thread's queue) contribute exactly 0 whatever their level is
+        if (ms.x == 0.f && ms.y == 0.f) return;
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
             const float2 dx = add2(xs, nx[t]), dy = add2(ys, ny[t]);
@@ -207,15 +210,18 @@ struct ForceF32 {
     }
 
     // Main loop without a branch: every iteration (one source pair x IPT targets) takes the fast lookup; an iteration
-    // with a d² in doubt pushes its index into a 4-entry queue held in ONE register (predicated LEA + IADD).  The queue
-    // is drained after the chunk, adding (g_exact − g_fast)·m·d for the queued iterations; more than 4 doubtful
-    // iterations in a chunk (only tables whose levels are denser than floats) redo the whole chunk on the slow path.
+    // with a d² in doubt pushes its index into an 8-entry queue held in TWO registers (predicated funnel shift, LEA,
+    // IADD).  The queue is drained after the chunk, adding (g_exact − g_fast)·m·d for the queued iterations.  A thread
+    // sees 0.26 doubtful iterations per chunk on average (L = 256), so more than 8 happen about once in 10¹¹
+    // thread-chunks for ordinary tables (a 4-entry queue overflowed 1.6 times per launch at N = 10⁴ and the straggling
+    // CTA doubled the kernel time); tables whose levels are denser than floats overflow always and redo every chunk
+    // on the slow path.
     template <bool CLAMP>
     __device__ __forceinline__ void chunk_lutf(const unsigned char* s) {
         const float4* A = reinterpret_cast<const float4*>(s);
         const float4* B4 = reinterpret_cast<const float4*>(s + kChunkABytes);
         const float2* B2 = reinterpret_cast<const float2*>(s + kChunkABytes);
-        uint32_t queue = 0, queued = 0;
+        uint32_t q0 = 0, q1 = 0, queued = 0;
 #pragma unroll UNROLL
         for (int p = 0; p < kChunkUnits; ++p) {
             const float4 a = A[p];
@@ -236,15 +242,15 @@ struct ForceF32 {
                 ay[t] = fma2(w, dy, ay[t]);
                 if (DIM == 3) az[t] = fma2(w, dz, az[t]);
             }
-            if (doubt) { queue = (queue << 8) + (uint32_t)p; ++queued; }
+            if (doubt) { q1 = __funnelshift_l(q0, q1, 8); q0 = (q0 << 8) + (uint32_t)p; ++queued; }
         }
         if (queued) {
-            if (queued > 4u) {
+            if (queued > 8u) {
 #pragma unroll
                 for (int t = 0; t < IPT; ++t) ax[t] = ay[t] = az[t] = make_float2(0.f, 0.f);
                 for (int p = 0; p < kChunkUnits; ++p) lutf_redo<true, CLAMP>(s, p);
             } else {
-                for (; queued; --queued, queue >>= 8) lutf_redo<false, CLAMP>(s, (int)(queue & 0xffu));
+                for (; queued; --queued, q0 = __funnelshift_r(q0, q1, 8), q1 >>= 8) lutf_redo<false, CLAMP>(s, (int)(q0 & 0xffu));
             }
         }
         flush();
@@ -611,18 +617,20 @@ extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_t
 
     int splits = 0, rc = NB_ERR_INVALID_ARGUMENT;
     constexpr int TH = kForceThreads, IPT = kForceIPT;
-    // uniform-mass fast path exists for the two headline kernels (fp32 state/FLOAT32, fp64 state/FLOAT64)
-    const bool uni = uniform_mass != 0 && ((dtype == NB_F32 && mode == NB_MODE_FLOAT32) || (dtype == NB_F64 && mode == NB_MODE_FLOAT64));
+    // uniform-mass fast path: fp32 state in FLOAT32 / FLOAT16 / BFLOAT16 mode, fp64 state in FLOAT64 mode
+    const bool uni = uniform_mass != 0 && ((dtype == NB_F32 && (mode == NB_MODE_FLOAT32 || mode == NB_MODE_FLOAT16 || mode == NB_MODE_BFLOAT16)) ||
+                                           (dtype == NB_F64 && mode == NB_MODE_FLOAT64));
+#define NB_F32_UNI_CASE(D, Q) rc = launch_accel<ForceF32<D, Q, IPT, TH, true>, 0>(a, workspace_bytes, st, &splits)
 #define NB_F32_CASE(D, Q, LUT) rc = launch_accel<ForceF32<D, Q, IPT, TH>, LUT>(a, workspace_bytes, st, &splits)
 #define NB_F64_CASE(D, Q) rc = launch_accel<ForceF64<D, Q, IPT, TH>, 0>(a, workspace_bytes, st, &splits)
     if (dtype == NB_F32) {
         if (mode == NB_MODE_FLOAT64) {
             if (dim == 2) rc = launch_accel<ForceMixed<2, IPT, TH>, 0>(a, workspace_bytes, st, &splits);
             else rc = launch_accel<ForceMixed<3, IPT, TH>, 0>(a, workspace_bytes, st, &splits);
-        } else if (mode == NB_MODE_FLOAT32 && uni) {
-            if (dim == 2) rc = launch_accel<ForceF32<2, Q_F32, IPT, TH, true>, 0>(a, workspace_bytes, st, &splits);
-            else rc = launch_accel<ForceF32<3, Q_F32, IPT, TH, true>, 0>(a, workspace_bytes, st, &splits);
-        } else if (mode == NB_MODE_FLOAT32) { if (dim == 2) NB_F32_CASE(2, Q_F32, 0); else NB_F32_CASE(3, Q_F32, 0); }
+        } else if (mode == NB_MODE_FLOAT32 && uni) { if (dim == 2) NB_F32_UNI_CASE(2, Q_F32); else NB_F32_UNI_CASE(3, Q_F32); }
+        else if (mode == NB_MODE_FLOAT16 && uni) { if (dim == 2) NB_F32_UNI_CASE(2, Q_F16); else NB_F32_UNI_CASE(3, Q_F16); }
+        else if (mode == NB_MODE_BFLOAT16 && uni) { if (dim == 2) NB_F32_UNI_CASE(2, Q_BF16); else NB_F32_UNI_CASE(3, Q_BF16); }
+        else if (mode == NB_MODE_FLOAT32) { if (dim == 2) NB_F32_CASE(2, Q_F32, 0); else NB_F32_CASE(3, Q_F32, 0); }
         else if (mode == NB_MODE_FLOAT16) { if (dim == 2) NB_F32_CASE(2, Q_F16, 0); else NB_F32_CASE(3, Q_F16, 0); }
         else if (mode == NB_MODE_BFLOAT16) { if (dim == 2) NB_F32_CASE(2, Q_BF16, 0); else NB_F32_CASE(3, Q_BF16, 0); }
         else if (levels <= kLutFastMaxLevels) {
@@ -640,6 +648,7 @@ extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_t
         else if (mode == NB_MODE_BFLOAT16) { if (dim == 2) NB_F64_CASE(2, Q_BF16); else NB_F64_CASE(3, Q_BF16); }
     }
 #undef NB_F32_CASE
+#undef NB_F32_UNI_CASE
 #undef NB_F64_CASE
     if (rc != NB_OK) return rc;
 

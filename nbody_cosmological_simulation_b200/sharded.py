@@ -153,12 +153,12 @@ class ShardedGalaxySimulation:
         """(all masses equal on every rank, value): local min/max, all-reduced; cached per masses tensor version."""
         m = self.masses
         key = (m.data_ptr(), m._version)
-        if getattr(self, "_uni_key", None) != key:
+        if getattr(self, "_uni_key", None) != key or getattr(self, "_uni_ref", None) is not m:
             lo, hi = torch.aminmax(m)
             mm = torch.stack([-lo.double(), hi.double()])
             self._all_reduce(mm, dist.ReduceOp.MAX)
             lo, hi = -mm[0].item(), mm[1].item()
-            self._uni_key, self._uni_val = key, (lo == hi, float(lo))
+            self._uni_key, self._uni_val, self._uni_ref = key, (lo == hi, float(lo)), m   # holding m pins its address
         return self._uni_val
 
     def _snap_now(self):

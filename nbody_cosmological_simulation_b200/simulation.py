@@ -16,6 +16,7 @@ SURVEY.md Appendix A.  There is no CPU path: CPU tensors raise.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Callable, Optional
 
 import numpy as np
@@ -25,6 +26,7 @@ from . import _lib as L
 from . import overrides
 from .quantization import PrecisionMode, levels_for_mode
 
+_UNIFORM_MASS_MODES = (PrecisionMode.FLOAT32, PrecisionMode.FLOAT64, PrecisionMode.FLOAT16, PrecisionMode.BFLOAT16)
 _INT_FORCE_SNAP = {PrecisionMode.INT8_SIM: 256, PrecisionMode.INT4_SIM: 16}      # simulation.py:115
 
 
@@ -145,9 +147,27 @@ class GalaxySimulation:
             self._packed_key = key
         return packed
 
+    class _PackedKey:
+        """Identity of the (x, m) a packed buffer was built from.  Weak references pin the tensor OBJECTS: an address
+        alone can be recycled by the caching allocator for a new tensor (same data_ptr, version 0) after the user
+        re-assigns `positions`."""
+
+        def __init__(self, x, m, packed):
+            self.refs = (weakref.ref(x), weakref.ref(m))
+            self.facts = (x._version, m._version, x.data_ptr(), m.data_ptr(), x.dtype, tuple(x.shape), packed.data_ptr())
+
+        def __eq__(self, other):
+            return isinstance(other, GalaxySimulation._PackedKey) and self.facts == other.facts and \
+                all(a() is not None and a() is b() for a, b in zip(self.refs, other.refs))
+
+        def __ne__(self, other):
+            return not self.__eq__(other)
+
+        __hash__ = None
+
     @staticmethod
     def _packed_cache_key(x, m, packed):
-        return (x.data_ptr(), x._version, m.data_ptr(), m._version, x.dtype, tuple(x.shape), packed.data_ptr())
+        return GalaxySimulation._PackedKey(x, m, packed)
 
     # ------------------------------------------------------------------------------------------
     # force evaluation — reference simulation.py:74-118
@@ -166,7 +186,7 @@ class GalaxySimulation:
         ws = buf.bytes("accel_ws", ws_bytes)
         eps_sq = float(self.softening_sq)
         table = None
-        uni, m0 = L.uniform_mass(m) if mode in (PrecisionMode.FLOAT32, PrecisionMode.FLOAT64) else (False, 0.0)
+        uni, m0 = L.uniform_mass(m) if mode in _UNIFORM_MASS_MODES else (False, 0.0)
         with torch.cuda.device(x.device):
             st = L.stream_ptr(x.device)
             if levels:
@@ -271,7 +291,7 @@ class GalaxySimulation:
         x, v, a = torch.empty_like(x_in), torch.empty_like(v_in), torch.empty_like(a_in)
         n, dim = x.shape
         code = L.dtype_code(x)
-        uni, m0 = L.uniform_mass(m) if mode in (PrecisionMode.FLOAT32, PrecisionMode.FLOAT64) else (False, 0.0)
+        uni, m0 = L.uniform_mass(m) if mode in _UNIFORM_MASS_MODES else (False, 0.0)
         packed = buf.bytes(f"packed{code}", lib.nb_packed_bytes(n, dim, code))
         table = buf.bytes("level_table", lib.nb_level_table_bytes(levels)) if levels else None
         ws = buf.bytes("accel_ws", max(lib.nb_accel_workspace_bytes(n, dim),

@@ -202,3 +202,26 @@ def test_pruned_max_dist_is_bit_exact(shape, dim):
     assert 1 <= count <= n
     if shape in ("disk", "cluster_far", "line"):
         assert count < n // 4                                             # the pruning actually prunes
+
+
+def test_caches_survive_recycled_tensor_addresses():
+    """The caching allocator hands a freed tensor's address to the next tensor of that size: state re-assigned by the
+    user (attributes may be re-assigned between ticks) must never be served from a cache keyed on the
+    old tensor's address (packed source records, uniform-mass flag)."""
+    import gc
+    import nbody_cosmological_simulation_b200 as nb
+    pos, vel, m = inputs(512, 2, torch.float32, seed=21, masses="random")
+    sim = nb.GalaxySimulation(pos.to(DEV), vel.to(DEV), torch.ones(512, device=DEV), precision_mode=nb.PrecisionMode.FLOAT32)
+    for trial in range(8):
+        old_x, old_m = sim.positions.data_ptr(), sim.masses.data_ptr()
+        sim.positions = None
+        sim.masses = None
+        gc.collect()
+        scale = 1.0 + 0.25 * (trial + 1)
+        sim.positions = pos.to(DEV) * scale                       # fresh tensors, version 0, very likely the old addresses
+        sim.masses = m.to(DEV) * scale                            # non-uniform now; the dead tensor was uniform
+        got = sim._compute_accelerations()
+        ref = ora.State(pos * scale, vel, m * scale, mode="float32")
+        assert_forces_close(got.cpu(), ref.acc, pos * scale, m * scale, 0.001, 0.1, 1e-5, 2.0 ** -24)
+        if sim.positions.data_ptr() == old_x and sim.masses.data_ptr() == old_m:
+            break
