@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 #include "stream.cuh"
 #include "lut.cuh"
+#include "internal.cuh"
 
 namespace nb {
 
@@ -525,7 +526,8 @@ __global__ void __launch_bounds__(256) accel_finalize_kernel(const double* __res
     long long kmin = kKeyHighest, kmax = kKeyLowest;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
         double s = 0.0;
-        for (int sp = 0; sp < splits; ++sp) s += partial[(int64_t)sp * count + e];
+#pragma unroll 8
+        for (int sp = 0; sp < splits; ++sp) s += partial[(int64_t)sp * count + e];        // loads batched, adds in split order
         const TOUT v = (TOUT)(s * scale);
         out[e] = v;
         if (MINMAX) {
@@ -590,11 +592,10 @@ extern "C" int64_t nb_accel_workspace_bytes(int64_t n_targets, int dim) {
     return (int64_t)max_splits_for(n_targets, dim) * n_targets * dim * (int64_t)sizeof(double);
 }
 
-extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt, int dim, int dtype,
-                        int mode, double G, double eps_sq, const void* level_table, int levels, int uniform_mass,
-                        double mass_value, void* acc_out,
-                        int64_t* scalars, void* workspace, int64_t workspace_bytes, void* stream) {
-    if (!packed_src || !pos_tgt || !acc_out || !workspace || n_src <= 0 || n_tgt <= 0 || (dim != 2 && dim != 3))
+int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt, int dim, int dtype, int mode,
+                    double G, double eps_sq, const void* level_table, int levels, int uniform_mass, double mass_value,
+                    int64_t* scalars, void* workspace, int64_t workspace_bytes, cudaStream_t st, PartialSums* out) {
+    if (!packed_src || !pos_tgt || !workspace || n_src <= 0 || n_tgt <= 0 || (dim != 2 && dim != 3))
         return NB_ERR_INVALID_ARGUMENT;
     if (dtype != NB_F32 && dtype != NB_F64) return NB_ERR_INVALID_ARGUMENT;
     if (mode < NB_MODE_FLOAT64 || mode > NB_MODE_CUSTOM) return NB_ERR_INVALID_ARGUMENT;
@@ -602,7 +603,6 @@ extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_t
     if (lut && (!level_table || levels < 2 || !scalars)) return NB_ERR_INVALID_ARGUMENT;
     if (lut && levels > kMaxLevelsSmem) return NB_ERR_UNSUPPORTED;
     if (lut && dtype == NB_F64) return NB_ERR_UNSUPPORTED;       // fp64 state + int modes: no caller in the reference
-    cudaStream_t st = (cudaStream_t)stream;
 
     AccelArgs a{};
     a.src = (const char*)packed_src;
@@ -651,18 +651,36 @@ extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_t
 #undef NB_F32_UNI_CASE
 #undef NB_F64_CASE
     if (rc != NB_OK) return rc;
+    // what the reduction needs: Σ splits, ×G (float modes: G was hoisted out of the pair loop; LUT factors carry G)
+    out->partial = a.partial;
+    out->splits = splits;
+    out->count = n_tgt * dim;
+    out->scale = lut ? 1.0 : (uni ? G * mass_value : G);
+    out->out_f64 = dtype == NB_F64 || mode == NB_MODE_FLOAT64;
+    out->minmax = mode == NB_MODE_INT8_SIM || mode == NB_MODE_INT4_SIM;
+    return NB_OK;
+}
 
-    // finalize: Σ splits, ×G (float modes: G was hoisted out of the pair loop; LUT factors already carry G)
-    const bool out_f64 = dtype == NB_F64 || mode == NB_MODE_FLOAT64;
-    const bool minmax = mode == NB_MODE_INT8_SIM || mode == NB_MODE_INT4_SIM;
-    const double scale = lut ? 1.0 : (uni ? G * mass_value : G);
-    const int64_t count = n_tgt * dim;
-    int64_t blocks = (count + 255) / 256;
+int nb::accel_reduce(const PartialSums& p, void* acc_out, int64_t* scalars, cudaStream_t st) {
+    if (!acc_out) return NB_ERR_INVALID_ARGUMENT;
+    int64_t blocks = (p.count + 255) / 256;
     if (blocks > kNumSMsB200 * 8) blocks = kNumSMsB200 * 8;
-    if (out_f64) accel_finalize_kernel<double, false><<<(int)blocks, 256, 0, st>>>(a.partial, splits, count, scale, (double*)acc_out, scalars);
-    else if (minmax) accel_finalize_kernel<float, true><<<(int)blocks, 256, 0, st>>>(a.partial, splits, count, scale, (float*)acc_out, scalars);
-    else accel_finalize_kernel<float, false><<<(int)blocks, 256, 0, st>>>(a.partial, splits, count, scale, (float*)acc_out, scalars);
+    if (p.out_f64) accel_finalize_kernel<double, false><<<(int)blocks, 256, 0, st>>>(p.partial, p.splits, p.count, p.scale, (double*)acc_out, scalars);
+    else if (p.minmax) accel_finalize_kernel<float, true><<<(int)blocks, 256, 0, st>>>(p.partial, p.splits, p.count, p.scale, (float*)acc_out, scalars);
+    else accel_finalize_kernel<float, false><<<(int)blocks, 256, 0, st>>>(p.partial, p.splits, p.count, p.scale, (float*)acc_out, scalars);
     NB_CUDA_LAUNCH_CHECK();
     return NB_OK;
+}
+
+extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt, int dim, int dtype,
+                        int mode, double G, double eps_sq, const void* level_table, int levels, int uniform_mass,
+                        double mass_value, void* acc_out,
+                        int64_t* scalars, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!acc_out) return NB_ERR_INVALID_ARGUMENT;
+    PartialSums p{};
+    const int rc = accel_pairs(packed_src, n_src, pos_tgt, n_tgt, dim, dtype, mode, G, eps_sq, level_table, levels, uniform_mass,
+                               mass_value, scalars, workspace, workspace_bytes, (cudaStream_t)stream, &p);
+    if (rc != NB_OK) return rc;
+    return accel_reduce(p, acc_out, scalars, (cudaStream_t)stream);
 }
 #endif  // NB_TUNE_HARNESS

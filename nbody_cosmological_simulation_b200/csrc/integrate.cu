@@ -3,6 +3,7 @@
 // HBM-bound elementwise work: one thread per "unit" (two fp32 particles / one fp64 particle), every
 // array read once and written once per tick, contiguous per warp.
 #include "common.cuh"
+#include "internal.cuh"
 
 namespace nb {
 
@@ -86,11 +87,25 @@ __global__ void __launch_bounds__(256) pack_kernel(const T* __restrict__ pos, co
 }
 
 // ---- nb_kdk ----------------------------------------------------------------------------------------
+// Optional source of the accelerations: the j-split partial sums of the force kernel, reduced on the fly in the
+// fixed split order and with the same `(T)(Σ·scale)` rounding as accel_finalize_kernel (bit-identical), and written
+// to `acc` so that the attribute stays observable.  partial == nullptr: `acc` is read as before.
+struct PartialSrc { const double* partial; int splits; int64_t count; double scale; };
+
+template <typename T>
+__device__ __forceinline__ T reduce_partial(const PartialSrc& ps, int64_t e) {
+    double s = 0.0;
+#pragma unroll 8
+    for (int sp = 0; sp < ps.splits; ++sp) s += ps.partial[(int64_t)sp * ps.count + e];   // loads batched, adds in split order
+    return (T)(s * ps.scale);
+}
+
 template <typename T, int DIM, typename TM, int PHASE>
 __global__ void __launch_bounds__(256) kdk_kernel(const T* __restrict__ x_in, const T* __restrict__ v_in, T* __restrict__ acc,
                                                   T* __restrict__ x_out, T* __restrict__ v_out, int64_t n, T half_dt, T dt,
                                                   int snap_levels, const int64_t* __restrict__ scalars,
-                                                  const TM* __restrict__ mass, char* __restrict__ packed, int64_t n_units) {
+                                                  const TM* __restrict__ mass, char* __restrict__ packed, int64_t n_units,
+                                                  const PartialSrc ps) {
     constexpr int UP = sizeof(T) == 4 ? 2 : 1;
     LinearGrid<T> grid(scalars, NB_SLOT_ACC_MIN, NB_SLOT_ACC_MAX, snap_levels > 0 ? snap_levels : 2);
     const bool snap = snap_levels > 0;
@@ -106,8 +121,9 @@ __global__ void __launch_bounds__(256) kdk_kernel(const T* __restrict__ x_in, co
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) {
                     const int64_t e = i * DIM + k;
-                    T a = acc[e];
-                    if (snap) { a = grid.snap(a); acc[e] = a; }
+                    T a = ps.partial ? reduce_partial<T>(ps, e) : acc[e];
+                    if (snap) a = grid.snap(a);
+                    if (snap || ps.partial) acc[e] = a;
                     T v = v_in[e];
                     const T kick = mul_rn(a, half_dt);
                     v = add_rn(v, kick);                                     // simulation.py:141 / :132
@@ -151,7 +167,8 @@ template <typename T, int DIM, typename TM, int PHASE>
 __global__ void __launch_bounds__(256) kdk_vec_kernel(const T* __restrict__ x_in, const T* __restrict__ v_in, T* __restrict__ acc,
                                                       T* __restrict__ x_out, T* __restrict__ v_out, int64_t n, T half_dt, T dt,
                                                       int snap_levels, const int64_t* __restrict__ scalars,
-                                                      const TM* __restrict__ mass, char* __restrict__ packed, int64_t n_units) {
+                                                      const TM* __restrict__ mass, char* __restrict__ packed, int64_t n_units,
+                                                      const PartialSrc ps) {
     constexpr int UP = sizeof(T) == 4 ? 2 : 1;       // particles per unit
     constexpr int PPT = 2 * UP;                      // particles per thread
     constexpr int V = PPT * DIM;                     // values per thread and array
@@ -170,7 +187,7 @@ __global__ void __launch_bounds__(256) kdk_vec_kernel(const T* __restrict__ x_in
         if (nreal == PPT) {
 #pragma unroll
             for (int q = 0; q < NV; ++q) {
-                reinterpret_cast<VT*>(a)[q] = reinterpret_cast<const VT*>(acc + e0)[q];
+                if (!ps.partial) reinterpret_cast<VT*>(a)[q] = reinterpret_cast<const VT*>(acc + e0)[q];
                 reinterpret_cast<VT*>(v)[q] = reinterpret_cast<const VT*>(v_in + e0)[q];
                 if (PHASE != NB_KDK_KICK) reinterpret_cast<VT*>(x)[q] = reinterpret_cast<const VT*>(x_in + e0)[q];
             }
@@ -178,10 +195,32 @@ __global__ void __launch_bounds__(256) kdk_vec_kernel(const T* __restrict__ x_in
 #pragma unroll
             for (int e = 0; e < V; ++e) {
                 const bool ok = e < nreal * DIM;
-                a[e] = ok ? acc[e0 + e] : (T)0;
+                a[e] = (ok && !ps.partial) ? acc[e0 + e] : (T)0;
                 v[e] = ok ? v_in[e0 + e] : (T)0;
                 x[e] = (ok && PHASE != NB_KDK_KICK) ? x_in[e0 + e] : (T)0;
             }
+        }
+        if (ps.partial) {
+            // Σ over the j-splits, two doubles per load (e0 is even: V values per thread, V ∈ {4, 6, 8, 12})
+            double s[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) s[e] = 0.0;
+            if (nreal == PPT && (ps.count & 1) == 0) {          // rows of an even length keep the 16-byte alignment
+#pragma unroll 4
+                for (int sp = 0; sp < ps.splits; ++sp) {                   // loads of 4 splits in flight, adds in split order
+                    const double2* row = reinterpret_cast<const double2*>(ps.partial + (int64_t)sp * ps.count + e0);
+#pragma unroll
+                    for (int q = 0; q < V / 2; ++q) { const double2 d = row[q]; s[2 * q] += d.x; s[2 * q + 1] += d.y; }
+                }
+            } else {
+                for (int sp = 0; sp < ps.splits; ++sp) {
+#pragma unroll
+                    for (int e = 0; e < V; ++e)
+                        if (e < nreal * DIM) s[e] += ps.partial[(int64_t)sp * ps.count + e0 + e];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < V; ++e) a[e] = (T)(s[e] * ps.scale);
         }
 #pragma unroll
         for (int e = 0; e < V; ++e) {
@@ -194,7 +233,7 @@ __global__ void __launch_bounds__(256) kdk_vec_kernel(const T* __restrict__ x_in
         if (nreal == PPT) {
 #pragma unroll
             for (int q = 0; q < NV; ++q) {
-                if (snap) reinterpret_cast<VT*>(acc + e0)[q] = reinterpret_cast<VT*>(a)[q];
+                if (snap || ps.partial) reinterpret_cast<VT*>(acc + e0)[q] = reinterpret_cast<VT*>(a)[q];
                 reinterpret_cast<VT*>(v_out + e0)[q] = reinterpret_cast<VT*>(v)[q];
                 if (PHASE != NB_KDK_KICK) reinterpret_cast<VT*>(x_out + e0)[q] = reinterpret_cast<VT*>(x)[q];
             }
@@ -202,7 +241,7 @@ __global__ void __launch_bounds__(256) kdk_vec_kernel(const T* __restrict__ x_in
 #pragma unroll
             for (int e = 0; e < V; ++e) {
                 if (e < nreal * DIM) {
-                    if (snap) acc[e0 + e] = a[e];
+                    if (snap || ps.partial) acc[e0 + e] = a[e];
                     v_out[e0 + e] = v[e];
                     if (PHASE != NB_KDK_KICK) x_out[e0 + e] = x[e];
                 }
@@ -261,21 +300,24 @@ int launch_pack(const void* pos, const void* mass, int64_t n, void* packed, int6
 
 template <typename T, int DIM, typename TM, int PHASE>
 int launch_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_out, int64_t n, double dt,
-               int snap_levels, const int64_t* scalars, const void* mass, void* packed, int64_t total_chunks, cudaStream_t st) {
+               int snap_levels, const int64_t* scalars, const void* mass, void* packed, int64_t total_chunks, cudaStream_t st,
+               const PartialSrc ps = PartialSrc{nullptr, 0, 0, 0.0}) {
     constexpr int UP = sizeof(T) == 4 ? 2 : 1;
     // with packed output the padding units (rest of the last chunk, plus whole padding chunks) are written too
     const int64_t natural = nb_num_chunks(n, sizeof(T) == 4 ? NB_F32 : NB_F64);
     if (packed && total_chunks != 0 && total_chunks < natural) return NB_ERR_INVALID_ARGUMENT;
     const int64_t n_units = packed ? (total_chunks ? total_chunks : natural) * kChunkUnits : (n + UP - 1) / UP;
     auto aligned16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    if (aligned16(x_in) && aligned16(v_in) && aligned16(acc) && aligned16(x_out) && aligned16(v_out)) {
+    // small systems reducing partial sums on the fly are latency-bound: one unit per thread (twice the threads) there
+    const bool prefer_scalar = ps.partial != nullptr && n_units <= (int64_t)kNumSMsB200 * 256;
+    if (!prefer_scalar && aligned16(x_in) && aligned16(v_in) && aligned16(acc) && aligned16(x_out) && aligned16(v_out)) {
         kdk_vec_kernel<T, DIM, TM, PHASE><<<grid_for((n_units + 1) / 2, 256), 256, 0, st>>>(
             (const T*)x_in, (const T*)v_in, (T*)acc, (T*)x_out, (T*)v_out, n, (T)(dt / 2), (T)dt, snap_levels, scalars,
-            (const TM*)mass, (char*)packed, n_units);
+            (const TM*)mass, (char*)packed, n_units, ps);
     } else {
         kdk_kernel<T, DIM, TM, PHASE><<<grid_for(n_units, 256), 256, 0, st>>>(
             (const T*)x_in, (const T*)v_in, (T*)acc, (T*)x_out, (T*)v_out, n, (T)(dt / 2), (T)dt, snap_levels, scalars,
-            (const TM*)mass, (char*)packed, n_units);
+            (const TM*)mass, (char*)packed, n_units, ps);
     }
     NB_CUDA_LAUNCH_CHECK();
     return NB_OK;
@@ -299,9 +341,9 @@ extern "C" int nb_pack_sources(const void* pos, const void* mass, int64_t n, int
     return NB_ERR_INVALID_ARGUMENT;
 }
 
-extern "C" int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_out, int64_t n, int dim, int dtype,
-                      double dt, int phase, int snap_levels, const int64_t* scalars, const void* mass, int mass_dtype,
-                      void* packed_out, int64_t total_chunks, void* stream) {
+static int kdk_dispatch(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_out, int64_t n, int dim, int dtype,
+                        double dt, int phase, int snap_levels, const int64_t* scalars, const void* mass, int mass_dtype,
+                        void* packed_out, int64_t total_chunks, void* stream, const PartialSrc ps) {
     if (!v_in || !acc || !v_out || n <= 0 || (dim != 2 && dim != 3)) return NB_ERR_INVALID_ARGUMENT;
     if (phase != NB_KDK_KICK && (!x_in || !x_out)) return NB_ERR_INVALID_ARGUMENT;
     if (snap_levels < 0 || snap_levels == 1 || (snap_levels > 0 && !scalars)) return NB_ERR_INVALID_ARGUMENT;
@@ -311,7 +353,7 @@ extern "C" int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out
     if (!mass) mass_dtype = dtype;
 #define NB_KDK_CASE(T, DT, TM, MDT, D, PH)                                  \
     if (dtype == DT && mass_dtype == MDT && dim == D && phase == PH)        \
-        return launch_kdk<T, D, TM, PH>(x_in, v_in, acc, x_out, v_out, n, dt, snap_levels, scalars, mass, packed_out, total_chunks, st);
+        return launch_kdk<T, D, TM, PH>(x_in, v_in, acc, x_out, v_out, n, dt, snap_levels, scalars, mass, packed_out, total_chunks, st, ps);
 #define NB_KDK_PHASES(T, DT, TM, MDT, D) \
     NB_KDK_CASE(T, DT, TM, MDT, D, NB_KDK_KICK_DRIFT) NB_KDK_CASE(T, DT, TM, MDT, D, NB_KDK_KICK) NB_KDK_CASE(T, DT, TM, MDT, D, NB_KDK_KICK_KICK_DRIFT)
     NB_KDK_PHASES(float, NB_F32, float, NB_F32, 2) NB_KDK_PHASES(float, NB_F32, float, NB_F32, 3)
@@ -321,6 +363,23 @@ extern "C" int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out
 #undef NB_KDK_PHASES
 #undef NB_KDK_CASE
     return NB_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_out, int64_t n, int dim, int dtype,
+                      double dt, int phase, int snap_levels, const int64_t* scalars, const void* mass, int mass_dtype,
+                      void* packed_out, int64_t total_chunks, void* stream) {
+    return kdk_dispatch(x_in, v_in, acc, x_out, v_out, n, dim, dtype, dt, phase, snap_levels, scalars, mass, mass_dtype, packed_out,
+                        total_chunks, stream, PartialSrc{nullptr, 0, 0, 0.0});
+}
+
+int nb::kdk_from_partials(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_out, int64_t n, int dim, int dtype,
+                          double dt, int phase, const int64_t* scalars, const void* mass, int mass_dtype, void* packed_out,
+                          int64_t total_chunks, const PartialSums& p, cudaStream_t st) {
+    // the state dtype must be the dtype the reduction would have written (fp64 accelerations on fp32 state — FLOAT64
+    // mode, first tick — promote the state first; the caller handles that)
+    if (p.minmax || p.count != n * dim || p.out_f64 != (dtype == NB_F64)) return NB_ERR_INVALID_ARGUMENT;
+    return kdk_dispatch(x_in, v_in, acc, x_out, v_out, n, dim, dtype, dt, phase, 0, scalars, mass, mass_dtype, packed_out, total_chunks,
+                        (void*)st, PartialSrc{p.partial, p.splits, p.count, p.scale});
 }
 
 extern "C" int nb_snap_accelerations(void* acc, int64_t count, int acc_dtype, int levels, const int64_t* scalars, void* stream) {

@@ -1,9 +1,12 @@
 // Native tick loop: GalaxySimulation.run (simulation.py:145-158) for the stock force, as ONE call.
-// The reference dispatches ~23-55 ATen kernels per tick from Python; here a tick is 3 launches
-// (fused kick-kick-drift + packed emit, force, finalize; int modes add reset / max-d² / level table) issued
-// from C, and for long runs of small systems the tick body is captured once into a CUDA graph and replayed,
-// so the per-tick host cost is one cudaGraphLaunch.
+// The reference dispatches ~23-55 ATen kernels per tick from Python; here a steady-state tick of a float mode is
+// 2 launches — the kick-kick-drift kernel, which also reduces the j-split partial sums of the previous force pass
+// and emits the packed sources, and the pair kernel — issued from C (int modes: reset / max-d² / level table /
+// pair kernel / reduction with min-max, because the force snap needs the global extrema first).  For long runs
+// of small systems the tick body is captured once into a CUDA graph and replayed, so the per-tick host cost is
+// one cudaGraphLaunch.
 #include "common.cuh"
+#include "internal.cuh"
 
 using namespace nb;
 
@@ -16,11 +19,18 @@ struct TickArgs {
     void *packed, *table; int64_t* scalars; void* ws; int64_t ws_bytes;
 };
 
-// one tick body: [closing kick of the previous tick +] opening kick + drift (+ packed emit), then the force
-int enqueue_tick(const TickArgs& a, bool first, cudaStream_t st) {
+// one tick body: [closing kick of the previous tick +] opening kick + drift (+ packed emit), then the force.
+// Float modes (`deferred`): the pair kernel leaves partial sums in the workspace; their reduction is folded into
+// the next tick's kick kernel (or done by finish_tick after the last one) — bit-identical to reducing first.
+int enqueue_tick(const TickArgs& a, bool first, bool deferred, PartialSums* ps, cudaStream_t st) {
     const int phase = first ? NB_KDK_KICK_DRIFT : NB_KDK_KICK_KICK_DRIFT;
-    int rc = nb_kdk(first ? a.x_in : a.x, first ? a.v_in : a.v, first ? a.acc_in : a.acc, a.x, a.v, a.n, a.dim, a.dtype, a.dt, phase, first ? 0 : a.snap_levels, a.scalars, a.mass,
-                    a.mass_dtype, a.packed, 0, st);
+    int rc;
+    if (deferred && !first)
+        rc = kdk_from_partials(a.x, a.v, a.acc, a.x, a.v, a.n, a.dim, a.dtype, a.dt, phase, a.scalars, a.mass, a.mass_dtype, a.packed, 0,
+                               *ps, st);
+    else
+        rc = nb_kdk(first ? a.x_in : a.x, first ? a.v_in : a.v, first ? a.acc_in : a.acc, a.x, a.v, a.n, a.dim, a.dtype, a.dt, phase,
+                    first ? 0 : a.snap_levels, a.scalars, a.mass, a.mass_dtype, a.packed, 0, st);
     if (rc) return rc;
     if (a.levels > 0) {
         if ((rc = nb_reset_scalars(a.scalars, st))) return rc;
@@ -28,8 +38,16 @@ int enqueue_tick(const TickArgs& a, bool first, cudaStream_t st) {
         if ((rc = nb_max_dist_sq(a.packed, a.n, a.dim, a.dtype, a.eps_sq, a.scalars, a.ws, a.ws_bytes, st))) return rc;
         if ((rc = nb_build_level_table(a.scalars, a.dtype, a.eps_sq, a.min_dist_sq, a.G, a.levels, a.table, st))) return rc;
     }
-    return nb_accel(a.packed, a.n, a.x, a.n, a.dim, a.dtype, a.mode, a.G, a.eps_sq, a.table, a.levels, a.uniform, a.mass_value,
-                    a.acc, a.scalars, a.ws, a.ws_bytes, st);
+    PartialSums now{};
+    if ((rc = accel_pairs(a.packed, a.n, a.x, a.n, a.dim, a.dtype, a.mode, a.G, a.eps_sq, a.table, a.levels, a.uniform, a.mass_value,
+                          a.scalars, a.ws, a.ws_bytes, st, &now))) return rc;
+    if (deferred) {
+        // the plan (split count, scale) is a pure function of the arguments: every tick produces the same descriptor,
+        // which is what lets a captured tick body be replayed
+        *ps = now;
+        return NB_OK;
+    }
+    return accel_reduce(now, a.acc, a.scalars, st);
 }
 
 }  // namespace
@@ -44,7 +62,12 @@ extern "C" int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_
     // the first kick only reads acc_in (it is already snapped, so no snap/write-back happens on it)
     TickArgs a{x_in ? x_in : x, v_in ? v_in : v, acc_in ? const_cast<void*>(acc_in) : acc, x, v, acc, mass, n, dim, dtype, mass_dtype, mode, levels, snap_levels, G, eps_sq, min_dist_sq, dt,
                uniform_mass, mass_value, packed, level_table, scalars, workspace, workspace_bytes};
-    int rc = enqueue_tick(a, /*first=*/true, st);
+    // the reduction can ride on the next kick kernel when no global min/max is needed between the two (no force
+    // snap) and the accelerations have the state's dtype
+    const bool acc_f64 = dtype == NB_F64 || mode == NB_MODE_FLOAT64;
+    const bool deferred = snap_levels == 0 && acc_f64 == (dtype == NB_F64);
+    PartialSums ps{};
+    int rc = enqueue_tick(a, /*first=*/true, deferred, &ps, st);
     if (rc) return rc;
     int64_t remaining = ticks - 1;
     if (use_graph && remaining >= 4) {
@@ -56,7 +79,7 @@ extern "C" int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_
         cudaError_t e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
         if (e == cudaSuccess) {
-            rc = enqueue_tick(a, /*first=*/false, cap);
+            rc = enqueue_tick(a, /*first=*/false, deferred, &ps, cap);
             e = cudaStreamEndCapture(cap, &graph);
             if (rc == NB_OK && e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
         }
@@ -70,7 +93,8 @@ extern "C" int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_
         if (e != cudaSuccess) { cudaGetLastError(); return cuda_status(e); }
     }
     for (; remaining > 0; --remaining)
-        if ((rc = enqueue_tick(a, /*first=*/false, st))) return rc;
+        if ((rc = enqueue_tick(a, /*first=*/false, deferred, &ps, st))) return rc;
+    if (deferred && (rc = accel_reduce(ps, acc, scalars, st))) return rc;
     // closing half kick (with the force snap of INT8/INT4) so that the state is observable
     return nb_kdk(nullptr, v, acc, nullptr, v, n, dim, dtype, dt, NB_KDK_KICK, snap_levels, scalars, mass, mass_dtype, nullptr, 0, st);
 }
