@@ -482,7 +482,7 @@ constexpr int kMaxLevelsSmem = 4096;      // level table entries staged in share
 
 // LUTKIND: 0 = no level table, 1 = 16-byte entries replicated per bank group (Q_LUT), 2 = fast lookup (Q_LUTF)
 template <class Consumer, int LUTKIND>
-__global__ void __launch_bounds__(Consumer::THREADS + 32, LUTKIND == 2 ? NB_LUTF_MINB : 1) accel_kernel(const AccelArgs a) {
+__global__ void __launch_bounds__(Consumer::THREADS + 32, LUTKIND == 2 ? NB_LUTF_MINB : 0) accel_kernel(const AccelArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const bool is_consumer = threadIdx.x < Consumer::THREADS;
     const float4* lut_smem = nullptr;
