@@ -182,10 +182,13 @@ int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_in, void* x
 
 /* ---- energies: simulation.py:170-196 ------------------------------------------------------- */
 int64_t nb_energy_workspace_bytes(int64_t n_targets);
-/* out[0] = Σ_{i in targets} Σ_{j > i} m_i m_j / sqrt(d²_ij)  over UNORDERED pairs (double; the caller applies −G
+/* out[0] = this shard's part of Σ_{i<j} m_i m_j / sqrt(d²_ij) over UNORDERED pairs (double; the caller applies −G
  * and sums ranks).  The targets must be the sources tgt_offset .. tgt_offset+n_tgt−1 of the packed set (an i-range
- * shard).  With a chunk-aligned tgt_offset only the upper triangle is evaluated (half the pairs); a negative or
- * unaligned offset selects the full-matrix form ½ Σ_{j≠i}, which needs no index correspondence. */
+ * shard).  With a chunk-aligned tgt_offset every unordered pair is evaluated once, by the half-ring rule: with C
+ * chunks and δ = (source chunk − target chunk) mod C, a target takes a source chunk with weight 1 if 0 < 2δ < C and
+ * ½ if δ == 0 or 2δ == C — half the pairs of the full matrix, and the same amount of work for every target chunk,
+ * so equal-sized shards cost the same on every rank (the plain upper triangle gives rank 0 twice the mean).
+ * A negative or unaligned offset selects the full-matrix form ½ Σ_{j≠i}, which needs no index correspondence. */
 int nb_potential_energy(const void* packed_src, int64_t n_src, const void* pos_tgt, const void* mass_tgt,
                         int64_t n_tgt, int64_t tgt_offset, int dim, int dtype, int mass_dtype, double eps_sq,
                         double* out, void* workspace, int64_t workspace_bytes, void* stream);

@@ -13,14 +13,29 @@ namespace nb {
 // ---- potential: Σ_{i∈targets} m_i ( Σ_j m_j / sqrt(d²_ij) − m_i / sqrt(ε²) ) ---------------------------
 // The j == i term is removed by subtracting the identical expression (d² == ε² exactly when dx == 0), so
 // the pair loop carries no index compare; requires targets ⊂ sources (always true: i-range shards).
+// Half-ring partition of the unordered pairs at chunk granularity: with C chunks and δ = (q − p) mod C, target chunk p
+// takes source chunk q with weight 1 if 0 < 2δ < C, ½ if δ == 0 (its own square: both orders, self term removed
+// by the caller) or 2δ == C (C even: both sides take it), 0 otherwise — every unordered pair is counted exactly once
+// and every target chunk has the same amount of work, so an i-range shard on any rank costs the same (the plain
+// upper triangle gives rank 0 twice the mean).  ring == 0: no index correspondence between targets and sources;
+// every chunk gets ½ (the reference's full-matrix form ½ Σ_{j≠i}).
+__device__ __forceinline__ double pair_weight(int64_t own, int64_t q, int64_t ring) {
+    if (ring <= 0) return 0.5;
+    int64_t d = q - own;
+    if (d < 0) d += ring;
+    if (d == 0 || 2 * d == ring) return 0.5;
+    return 2 * d < ring ? 1.0 : 0.0;
+}
+
 template <int DIM_, int IPT, int THREADS_>
 struct PotentialF32 {
     static constexpr int DIM = DIM_;
     static constexpr int THREADS = THREADS_;
     float2 nx[IPT], ny[IPT], nz[IPT];
     float2 acc[IPT];
-    double sum[IPT], sum_diag[IPT];          // chunks strictly above the diagonal square / chunks inside it
-    int64_t diag_lo, diag_hi;                // chunk range of this CTA's diagonal square
+    double sum[IPT];                         // Σ over the streamed chunks of weight(own chunk, source chunk) · Σ_j m_j / r_ij
+    int64_t own_chunk[IPT];                  // global chunk index of target t
+    int64_t ring;                            // number of chunks of the source set (0: every chunk has weight ½)
     float2 eps2;
     __device__ __forceinline__ void init(const float* pos, int64_t n_tgt, float e2) {
 #pragma unroll
@@ -30,7 +45,7 @@ struct PotentialF32 {
             const float x = pos[i * DIM + 0], y = pos[i * DIM + 1], z = DIM == 3 ? pos[i * DIM + 2] : 0.f;
             nx[t] = make_float2(-x, -x); ny[t] = make_float2(-y, -y); nz[t] = make_float2(-z, -z);
             acc[t] = make_float2(0.f, 0.f);
-            sum[t] = sum_diag[t] = 0.0;
+            sum[t] = 0.0;
         }
         eps2 = make_float2(e2, e2);
     }
@@ -55,11 +70,9 @@ struct PotentialF32 {
                 acc[t] = fma2(ms, r, acc[t]);
             }
         }
-        const bool diag = chunk_index >= diag_lo && chunk_index < diag_hi;
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
-            const double c = (double)(acc[t].x + acc[t].y);
-            if (diag) sum_diag[t] += c; else sum[t] += c;
+            sum[t] += pair_weight(own_chunk[t], chunk_index, ring) * (double)(acc[t].x + acc[t].y);
             acc[t] = make_float2(0.f, 0.f);
         }
     }
@@ -77,8 +90,9 @@ struct PotentialF64 {
     static constexpr int DIM = DIM_;
     static constexpr int THREADS = THREADS_;
     double xi[IPT], yi[IPT], zi[IPT];
-    double sum[IPT], sum_diag[IPT];
-    int64_t diag_lo, diag_hi;
+    double sum[IPT];
+    int64_t own_chunk[IPT];
+    int64_t ring;
     double eps2;
     __device__ __forceinline__ void init(const double* pos, int64_t n_tgt, double e2) {
 #pragma unroll
@@ -86,7 +100,7 @@ struct PotentialF64 {
             int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i >= n_tgt) i = n_tgt - 1;
             xi[t] = pos[i * DIM + 0]; yi[t] = pos[i * DIM + 1]; zi[t] = DIM == 3 ? pos[i * DIM + 2] : 0.0;
-            sum[t] = sum_diag[t] = 0.0;
+            sum[t] = 0.0;
         }
         eps2 = e2;
     }
@@ -111,9 +125,8 @@ struct PotentialF64 {
                 part[t] = fma(m, rsqrt_full(d2), part[t]);
             }
         }
-        const bool diag = chunk_index >= diag_lo && chunk_index < diag_hi;
 #pragma unroll
-        for (int t = 0; t < IPT; ++t) { if (diag) sum_diag[t] += part[t]; else sum[t] += part[t]; }
+        for (int t = 0; t < IPT; ++t) sum[t] += pair_weight(own_chunk[t], chunk_index, ring) * part[t];
     }
 };
 
@@ -123,10 +136,10 @@ __global__ void __launch_bounds__(THREADS + 32) potential_kernel(const char* __r
                                                                  int64_t n_tgt, int64_t tgt_offset, int triangular,
                                                                  int chunks_per_split, double eps_sq,
                                                                  double* __restrict__ block_partials) {
-    // Unordered pairs: out = Σ_{i<j} m_i m_j / r_ij.  With chunk-aligned targets (triangular != 0) a CTA skips every
-    // source chunk below its own targets, counts chunks above them once, and counts the diagonal square (sources that
-    // are its own targets) with weight ½ after removing the j == i term.  Otherwise every chunk is "diagonal":
-    // ½ Σ_{j≠i}, the reference's full-matrix form.
+    // Unordered pairs: out = Σ_{i<j} m_i m_j / r_ij.  With chunk-aligned targets (triangular != 0) a CTA streams the
+    // half ring of source chunks that starts at its own first chunk (pair_weight above); its own squares carry the
+    // j == i term, which is removed below.  Otherwise every chunk has weight ½: ½ Σ_{j≠i}, the reference's
+    // full-matrix form.
     __shared__ double red[32];
     constexpr int TB = THREADS * IPT;
     constexpr int CS = sizeof(T) == 4 ? 2 * kChunkUnits : kChunkUnits;       // sources per chunk
@@ -135,16 +148,22 @@ __global__ void __launch_bounds__(THREADS + 32) potential_kernel(const char* __r
     Cons cons;
     const bool is_consumer = threadIdx.x < THREADS;
     if (is_consumer) cons.init(pos_tgt, n_tgt, (T)eps_sq);
-    int64_t c0 = (int64_t)blockIdx.y * chunks_per_split;
-    const int64_t c1 = min(n_chunks, c0 + (int64_t)chunks_per_split);
     const int64_t first_tgt = tgt_offset + (int64_t)blockIdx.x * TB;
-    cons.diag_lo = triangular ? first_tgt / CS : 0;
-    // the diagonal square ends with this block's REAL targets (a partial last block must not claim the chunks of the
-    // next rank's slot); the tail of its last chunk is padding (mass 0)
+    const int64_t g0 = triangular ? first_tgt / CS : 0;                       // first chunk of this block's targets
+    // the block's own chunks end with its REAL targets (a partial last block must not reach into the next rank's slot)
     const int64_t blk_tgts = min((int64_t)TB, n_tgt - (int64_t)blockIdx.x * TB);
-    cons.diag_hi = triangular ? (first_tgt + blk_tgts + CS - 1) / CS : n_chunks;
-    if (c0 < cons.diag_lo) c0 = cons.diag_lo;                         // pairs with j < i are counted by the other side
-    stream_sources(src, c0, c1 > c0 ? c1 : c0, cons);
+    const int64_t own_chunks = (blk_tgts + CS - 1) / CS;
+    const int64_t span = triangular ? min(n_chunks, own_chunks + n_chunks / 2) : n_chunks;   // ring offsets this block needs
+    const int64_t c0 = min(span, (int64_t)blockIdx.y * chunks_per_split);
+    const int64_t c1 = min(span, c0 + (int64_t)chunks_per_split);
+    cons.ring = triangular ? n_chunks : 0;
+#pragma unroll
+    for (int t = 0; t < IPT; ++t) {
+        int64_t i = (int64_t)blockIdx.x * TB + t * THREADS + (is_consumer ? threadIdx.x : 0);
+        if (i >= n_tgt) i = n_tgt - 1;
+        cons.own_chunk[t] = (tgt_offset + i) / CS;
+    }
+    stream_sources(src, g0 + c0, g0 + c1, cons, triangular ? n_chunks : 0);
     double mine = 0.0;
     if (is_consumer) {
 #pragma unroll
@@ -152,15 +171,15 @@ __global__ void __launch_bounds__(THREADS + 32) potential_kernel(const char* __r
             const int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i < n_tgt) {
                 const double m = (double)mass_tgt[i];
-                double sd = cons.sum_diag[t];
-                const int64_t self_chunk = (tgt_offset + i) / CS;      // the j == i term lives in exactly one j-split
-                if (self_chunk >= c0 && self_chunk < c1) {
+                double sd = cons.sum[t];
+                const int64_t self_off = cons.own_chunk[t] - g0;       // the j == i term lives in exactly one j-split
+                if (self_off >= c0 && self_off < c1) {
                     double self;
                     if constexpr (sizeof(T) == 4) self = (double)((float)m * rsqrt_approx((float)eps_sq));
                     else self = m * rsqrt_full(eps_sq);
-                    sd -= self;
+                    sd -= 0.5 * self;                                  // its square was taken with weight ½
                 }
-                mine += m * (cons.sum[t] + 0.5 * sd);
+                mine += m * sd;
             }
         }
     }
@@ -282,11 +301,14 @@ static int launch_potential(const void* packed_src, int64_t n_src, const void* p
     int occ = 1;
     const int frc = kernel_occupancy((const void*)k, TH + 32, smem, &occ);
     if (frc != NB_OK) return frc;
-    const SplitPlan sp = plan_splits(n_tgt, n_chunks, TH * IPT, occ, 64);
+    const int triangular = tgt_offset >= 0 && tgt_offset % nb_chunk_sources(dtype) == 0;
+    // chunks a target block streams: its own plus half the ring (all of them in the full-matrix form)
+    const int64_t own = (TH * IPT) / nb_chunk_sources(dtype);
+    const int64_t span = triangular ? (own + n_chunks / 2 < n_chunks ? own + n_chunks / 2 : n_chunks) : n_chunks;
+    const SplitPlan sp = plan_splits(n_tgt, span, TH * IPT, occ, 64);
     const int blocks_i = sp.blocks_i, cps = sp.chunks_per_split, splits = sp.splits;
     const int64_t ctas = (int64_t)blocks_i * splits;
     if (workspace_bytes < ctas * (int64_t)sizeof(double)) return NB_ERR_WORKSPACE_TOO_SMALL;
-    const int triangular = tgt_offset >= 0 && tgt_offset % nb_chunk_sources(dtype) == 0;
     k<<<dim3(blocks_i, splits), TH + 32, smem, st>>>((const char*)packed_src, n_chunks, (const T*)pos_tgt, (const TM*)mass_tgt, n_tgt,
                                                     triangular ? tgt_offset : 0, triangular, cps, eps_sq, (double*)workspace);
     NB_CUDA_LAUNCH_CHECK();

@@ -103,8 +103,12 @@ inline int kernel_occupancy(const void* fn, int threads, int smem, int* occ_out)
 // Consumer concept:
 //   static constexpr int DIM, THREADS (consumer threads; the CTA has THREADS + 32);
 //   __device__ void chunk(const unsigned char* smem_chunk, int64_t chunk_index);   // all consumer threads
+// `ring` > 0: chunk indices are taken modulo `ring` (the range [c0, c1) may run past the last chunk and continue at
+// chunk 0 — the half-ring partition of the potential-energy pairs); a stage that straddles the wrap point is filled
+// by two bulk copies counted on the same barrier.
 template <class Consumer>
-__device__ __forceinline__ void stream_sources(const char* __restrict__ src, int64_t c0, int64_t c1, Consumer& cons) {
+__device__ __forceinline__ void stream_sources(const char* __restrict__ src, int64_t c0, int64_t c1, Consumer& cons,
+                                               int64_t ring = 0) {
     constexpr int DIM = Consumer::DIM;
     constexpr int NCW = Consumer::THREADS / 32;     // consumer warps
     extern __shared__ __align__(128) unsigned char smem[];
@@ -139,7 +143,12 @@ __device__ __forceinline__ void stream_sources(const char* __restrict__ src, int
                 const int cnt = min(kStageChunks, n_chunks - first);
                 const uint32_t bytes = (uint32_t)(cnt * cb);
                 mbar_arrive_expect_tx(bar0 + 8 * s, bytes);
-                tma_bulk_g2s(smem_u32(data + s * kStageChunks * cb), src + (c0 + first) * (int64_t)cb, bytes, bar0 + 8 * s);
+                int64_t g = c0 + first;
+                int head = cnt;
+                if (ring > 0) { g %= ring; if (g + cnt > ring) head = (int)(ring - g); }
+                tma_bulk_g2s(smem_u32(data + s * kStageChunks * cb), src + g * (int64_t)cb, (uint32_t)(head * cb), bar0 + 8 * s);
+                if (head < cnt)
+                    tma_bulk_g2s(smem_u32(data + s * kStageChunks * cb + head * cb), src, (uint32_t)((cnt - head) * cb), bar0 + 8 * s);
             }
         }
     } else {
@@ -150,7 +159,11 @@ __device__ __forceinline__ void stream_sources(const char* __restrict__ src, int
             const int first = it * kStageChunks;
             const int cnt = min(kStageChunks, n_chunks - first);
             const unsigned char* stage = data + s * kStageChunks * cb;
-            for (int c = 0; c < cnt; ++c) cons.chunk(stage + c * cb, c0 + first + c);
+            for (int c = 0; c < cnt; ++c) {
+                int64_t g = c0 + first + c;
+                if (ring > 0) g %= ring;
+                cons.chunk(stage + c * cb, g);
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar0 + 8 * (kStages + s));
         }
