@@ -345,8 +345,8 @@ class GalaxySimulation:
         # the reference returns `.item()` of a tensor of this dtype
         return float(np.float32(value)) if dtype == torch.float32 else float(value)
 
-    def get_kinetic_energy(self) -> float:
-        """0.5·Σ m v² (reference simulation.py:170-174)."""
+    def _kinetic_sum_device(self):
+        """(Σ m v² as a 1-element fp64 device tensor, result dtype) — enqueued, no host synchronisation."""
         _, v, m = self._state()
         lib, buf = L.load(), self._buf()
         n, dim = v.shape
@@ -355,7 +355,12 @@ class GalaxySimulation:
         with torch.cuda.device(v.device):
             L.check(lib.nb_kinetic_energy(L.ptr(v), L.ptr(m), n, dim, L.dtype_code(v), L.dtype_code(m), L.ptr(out),
                                           L.ptr(ws), ws.numel(), L.stream_ptr(v.device)), "nb_kinetic_energy")
-        return self._as_python_float(0.5 * out.item(), torch.promote_types(v.dtype, m.dtype))
+        return out, torch.promote_types(v.dtype, m.dtype)
+
+    def get_kinetic_energy(self) -> float:
+        """0.5·Σ m v² (reference simulation.py:170-174)."""
+        out, dtype = self._kinetic_sum_device()
+        return self._as_python_float(0.5 * out.item(), dtype)
 
     def get_potential_energy(self) -> float:
         """−G·Σ_{i<j} m_i m_j / r_ij with softening (reference simulation.py:176-192)."""
@@ -367,6 +372,16 @@ class GalaxySimulation:
         cached = getattr(self, "_pe_cache", None)
         if cached is not None and cached[0] == key and cached[2] is x and cached[3] is m:
             return cached[1]
+        out, dtype = self._potential_sum_device(x, m)
+        # the kernel sums unordered pairs i < j
+        value = self._as_python_float(-float(self.G) * out.item(), dtype)
+        self._pe_cache = (key, value, x, m)       # holding x, m keeps their addresses from being recycled
+        return value
+
+    def _potential_sum_device(self, x=None, m=None):
+        """(Σ_{i<j} m_i m_j / r_ij as a 1-element fp64 device tensor, result dtype) — enqueued, no host synchronisation."""
+        if x is None:
+            x, _, m = self._state()
         lib, buf = L.load(), self._buf()
         n, dim = x.shape
         packed = self._pack(x, m)
@@ -376,10 +391,19 @@ class GalaxySimulation:
             L.check(lib.nb_potential_energy(L.ptr(packed), n, L.ptr(x), L.ptr(m), n, 0, dim, L.dtype_code(x),
                                             L.dtype_code(m), float(self.softening_sq), L.ptr(out), L.ptr(ws),
                                             ws.numel(), L.stream_ptr(x.device)), "nb_potential_energy")
-        # the kernel sums unordered pairs i < j
-        value = self._as_python_float(-float(self.G) * out.item(), torch.promote_types(x.dtype, m.dtype))
-        self._pe_cache = (key, value, x, m)       # holding x, m keeps their addresses from being recycled
-        return value
+        return out, torch.promote_types(x.dtype, m.dtype)
+
+    def _total_energy_deferred(self):
+        """A zero-argument callable that returns get_total_energy() of the CURRENT state; the kernels are enqueued now,
+        the two scalars are read when it is called (after a synchronisation of the caller's choosing)."""
+        ke, kdt = self._kinetic_sum_device()
+        pe, pdt = self._potential_sum_device()
+        ke_host = torch.empty(1, dtype=torch.float64, pin_memory=True)
+        pe_host = torch.empty(1, dtype=torch.float64, pin_memory=True)
+        ke_host.copy_(ke, non_blocking=True)
+        pe_host.copy_(pe, non_blocking=True)
+        G = float(self.G)
+        return lambda: self._as_python_float(0.5 * ke_host.item(), kdt) + self._as_python_float(-G * pe_host.item(), pdt)
 
     def get_total_energy(self) -> float:
         return self.get_kinetic_energy() + self.get_potential_energy()
@@ -395,21 +419,32 @@ def run_comparison(
     callback_interval: int = 100,
     **sim_kwargs,
 ) -> dict:
-    """Same initial conditions under several precision modes (reference simulation.py:199-250)."""
+    """Same initial conditions under several precision modes (reference simulation.py:199-250).
+
+    The reference's recorder copies the full position array to the host and pulls two energy scalars with `.item()`
+    at every callback, i.e. it drains the GPU each time.  Here the recorder only ENQUEUES: the positions go to pinned
+    host memory with an asynchronous copy, the energy kernels leave their scalars in pinned memory too, and
+    everything is read once after the run.  What the caller gets back is identical: CPU
+    tensors, Python floats, the same ticks.  A user `callback` still sees the live simulation at every interval."""
     results = {}
     for mode in modes:
         print(f"\nRunning simulation with {mode.value} precision...")
         sim = GalaxySimulation(positions.clone(), velocities.clone(), masses.clone(), precision_mode=mode,
                                **sim_kwargs)
-        history = {"positions": [positions.clone().cpu()], "energies": [sim.get_total_energy()], "ticks": [0]}
+        history = {"positions": [positions.clone().cpu()], "energies": [sim._total_energy_deferred()], "ticks": [0]}
 
         def record(s, tick, history=history):
-            history["positions"].append(s.positions.clone().cpu())
-            history["energies"].append(s.get_total_energy())
+            x = s.positions
+            host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+            host.copy_(x, non_blocking=True)                  # ordered after the tick's kernels on the same stream
+            history["positions"].append(host)
+            history["energies"].append(s._total_energy_deferred())
             history["ticks"].append(tick)
             if callback:
                 callback(s, tick)
 
         sim.run(num_ticks, callback=record, callback_interval=callback_interval)
+        torch.cuda.synchronize(sim.positions.device)
+        history["energies"] = [e() for e in history["energies"]]
         results[mode.value] = {"final_state": sim.get_state(), "history": history, "simulation": sim}
     return results

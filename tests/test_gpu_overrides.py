@@ -94,3 +94,31 @@ def test_unrecognised_override_still_runs_as_written(monkeypatch):
     assert torch.allclose(h.accelerations, 0.5 * s.accelerations, rtol=1e-6, atol=0)
     h.step(); s.step()
     assert not torch.allclose(h.velocities, s.velocities, rtol=1e-6, atol=0)      # the halved force really drove the kick
+
+
+def test_run_comparison_history_equals_the_reference_style_recorder():
+    """run_comparison (simulation.py:199-250) records with asynchronous pinned copies and deferred energy reads
+    (SURVEY.md §8f row 4); the history must equal what the reference's synchronous recorder produces."""
+    torch.manual_seed(4)
+    pos, vel, mass = nb.create_disk_galaxy(400, device=DEV)
+    modes = [nb.PrecisionMode.FLOAT32, nb.PrecisionMode.FLOAT64, nb.PrecisionMode.INT4_SIM]
+    seen = []
+    res = nb.run_comparison(pos, vel, mass, modes, num_ticks=60, callback=lambda s, t: seen.append((s.precision_mode.value, t)),
+                            callback_interval=20)
+    assert seen == [(m.value, t) for m in modes for t in (20, 40, 60)]
+    for mode in modes:
+        sim = nb.GalaxySimulation(pos.clone(), vel.clone(), mass.clone(), precision_mode=mode)
+        want = {"positions": [pos.clone().cpu()], "energies": [sim.get_total_energy()], "ticks": [0]}
+
+        def record(s, tick):
+            want["positions"].append(s.positions.clone().cpu())
+            want["energies"].append(s.get_total_energy())
+            want["ticks"].append(tick)
+        sim.run(60, callback=record, callback_interval=20)
+        got = res[mode.value]["history"]
+        assert got["ticks"] == want["ticks"] == [0, 20, 40, 60]
+        assert got["energies"] == want["energies"] and all(isinstance(e, float) for e in got["energies"])
+        for a, b in zip(got["positions"], want["positions"]):
+            assert a.device.type == "cpu" and a.dtype == b.dtype and torch.equal(a, b)
+        assert res[mode.value]["final_state"]["tick"] == 60 and res[mode.value]["simulation"].tick == 60
+        assert torch.equal(res[mode.value]["final_state"]["positions"], sim.positions)
