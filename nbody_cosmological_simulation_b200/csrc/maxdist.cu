@@ -18,7 +18,7 @@ struct MdHeader {                     // 128-byte workspace header, reset by md_
     unsigned dlb_bits;                // max d² from the far point (non-negative float bits)
     unsigned count;                   // number of candidates
     unsigned flags;                   // 1: NaN coordinate seen, 2: ±Inf coordinate seen
-    unsigned pad0;
+    unsigned found;                   // candidates found (kept when `count` is zeroed by the single-CTA path)
     unsigned long long far_key;       // (float bits of R² << 32) | index of the farthest point
     unsigned best_bits;               // max over candidate pairs of s (non-negative float bits)
     unsigned pad1[19];
@@ -40,7 +40,7 @@ __device__ __forceinline__ void load_source(const char* __restrict__ packed, int
 __global__ void md_init(MdHeader* h) {
     if (threadIdx.x == 0) {
         for (int k = 0; k < 3; ++k) { h->lo[k] = 0xffffffffu; h->hi[k] = 0u; }
-        h->dlb_bits = 0u; h->count = 0u; h->flags = 0u; h->far_key = 0ull; h->best_bits = 0u;
+        h->dlb_bits = 0u; h->count = 0u; h->flags = 0u; h->found = 0u; h->far_key = 0ull; h->best_bits = 0u;
     }
 }
 
@@ -167,13 +167,141 @@ __global__ void __launch_bounds__(256) md_pairs(const float4* __restrict__ cand,
     if ((threadIdx.x & 31) == 0) atomicMax(&h->best_bits, __float_as_uint(best));
 }
 
-__global__ void md_publish(const MdHeader* __restrict__ h, float eps2, int64_t* __restrict__ scalars) {
+__global__ void md_publish(MdHeader* __restrict__ h, float eps2, int64_t* __restrict__ scalars) {
     if (threadIdx.x == 0) {
+        if (h->count) h->found = h->count;
         float v = __fadd_rn(__uint_as_float(h->best_bits), eps2);      // rn(max s + ε²)
         if (h->flags & 2u) v = INFINITY;                                // torch.max semantics for non-finite inputs
         if (h->flags & 1u) v = __int_as_float(0x7fffffff);
         atomicMax(reinterpret_cast<long long*>(scalars + NB_SLOT_MAX_D2), (long long)key_from_double((double)v));
     }
+}
+
+// Small systems (n <= kMdSmallMax): the four O(n) phases above in ONE CTA with block barriers in between instead of
+// four launches + an init launch (a tick of a 10⁴-star int-mode run spent 25 µs in these seven tiny kernels).  The
+// arithmetic is the same, so the candidate SET is the same; if it is small the exact pairwise maximum is taken here
+// as well and `count` is zeroed so that md_pairs, launched afterwards as always, finds nothing left to do.
+constexpr int64_t kMdSmallMax = 32768;
+constexpr unsigned kMdSmallPairs = 1024;
+
+template <int DIM>
+__global__ void __launch_bounds__(1024) md_small(const char* __restrict__ packed, int64_t n, MdHeader* __restrict__ gh,
+                                                 float4* __restrict__ cand) {
+    __shared__ MdHeader h;
+    __shared__ float4 tile[256];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) {
+        for (int k = 0; k < 3; ++k) { h.lo[k] = 0xffffffffu; h.hi[k] = 0u; }
+        h.dlb_bits = 0u; h.count = 0u; h.flags = 0u; h.found = 0u; h.far_key = 0ull; h.best_bits = 0u;
+    }
+    __syncthreads();
+    {   // bounding box + non-finite flags (md_bbox)
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        unsigned flags = 0;
+        for (int64_t j = tid; j < n; j += blockDim.x) {
+            float p[3];
+            load_source<DIM>(packed, j, p[0], p[1], p[2]);
+            if (p[0] > kPadDetectF32) continue;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                if (p[k] != p[k]) flags |= 1u; else if (fabsf(p[k]) == INFINITY) flags |= 2u;
+                lo[k] = fminf(lo[k], p[k]); hi[k] = fmaxf(hi[k], p[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) { lo[k] = warp_reduce(lo[k], OpMin()); hi[k] = warp_reduce(hi[k], OpMax()); }
+        flags = __reduce_or_sync(0xffffffffu, flags);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) { atomicMin(&h.lo[k], fkey(lo[k])); atomicMax(&h.hi[k], fkey(hi[k])); }
+            if (flags) atomicOr(&h.flags, flags);
+        }
+    }
+    __syncthreads();
+    float c[3];
+    centre_of<DIM>(&h, c);
+    {   // farthest point from the centre (md_far_point)
+        unsigned long long best = 0ull;
+        for (int64_t j = tid; j < n; j += blockDim.x) {
+            float x, y, z;
+            load_source<DIM>(packed, j, x, y, z);
+            if (x > kPadDetectF32) continue;
+            const float r2 = (x - c[0]) * (x - c[0]) + (y - c[1]) * (y - c[1]) + (z - c[2]) * (z - c[2]);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(r2) << 32) | (unsigned long long)(unsigned)j;
+            if (r2 == r2 && key > best) best = key;
+        }
+        best = warp_reduce(best, OpMax());
+        if (lane == 0 && best) atomicMax(&h.far_key, best);
+    }
+    __syncthreads();
+    {   // its farthest partner: lower bound of the maximum (md_lower_bound)
+        float px, py, pz;
+        load_source<DIM>(packed, (int64_t)(h.far_key & 0xffffffffull), px, py, pz);
+        float best = 0.f;
+        for (int64_t j = tid; j < n; j += blockDim.x) {
+            float x, y, z;
+            load_source<DIM>(packed, j, x, y, z);
+            if (x > kPadDetectF32) continue;
+            best = fmaxf(best, (x - px) * (x - px) + (y - py) * (y - py) + (z - pz) * (z - pz));
+        }
+        best = warp_reduce(best, OpMax());
+        if (lane == 0) atomicMax(&h.dlb_bits, __float_as_uint(best));
+    }
+    __syncthreads();
+    {   // outer-shell candidates (md_compact)
+        const float rmax = sqrtf(__uint_as_float((unsigned)(h.far_key >> 32)));
+        const float dlb = sqrtf(__uint_as_float(h.dlb_bits));
+        const float thr = dlb * (1.f - 1e-4f) - rmax * (1.f + 1e-5f) - 1e-30f;
+        const int64_t n_round = (n + 31) / 32 * 32;
+        for (int64_t j = tid; j < n_round; j += blockDim.x) {
+            float x = 0.f, y = 0.f, z = 0.f;
+            bool keep = false;
+            if (j < n) {
+                load_source<DIM>(packed, j, x, y, z);
+                if (!(x > kPadDetectF32)) {
+                    const float r = sqrtf((x - c[0]) * (x - c[0]) + (y - c[1]) * (y - c[1]) + (z - c[2]) * (z - c[2]));
+                    keep = r >= thr;
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (mask) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&h.count, (unsigned)__popc(mask));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (keep) cand[base + __popc(mask & ((1u << lane) - 1u))] = make_float4(x, y, z, 0.f);
+            }
+        }
+    }
+    __syncthreads();                                   // candidates written by this block are visible to it
+    const unsigned count = h.count;
+    if (tid == 0) h.found = count;
+    if (count <= kMdSmallPairs) {
+        // exact pairwise maximum over the candidates (md_pairs), rows strided over the block
+        float best = 0.f;
+        for (unsigned ib = 0; ib < count; ib += blockDim.x) {
+            const unsigned i = ib + tid;
+            const float4 me = cand[i < count ? i : count - 1];
+            for (unsigned jb = 0; jb < count; jb += 256u) {
+                __syncthreads();
+                if (tid < 256) { const unsigned j = jb + tid; tile[tid] = cand[j < count ? j : count - 1]; }
+                __syncthreads();
+                const int lim = (int)min(256u, count - jb);
+                for (int t = 0; t < lim; ++t) {
+                    const float4 o = tile[t];
+                    const float dx = __fsub_rn(o.x, me.x), dy = __fsub_rn(o.y, me.y);
+                    float s = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));         // simulation.py:86 rounding order
+                    if (DIM == 3) { const float dz = __fsub_rn(o.z, me.z); s = __fadd_rn(s, __fmul_rn(dz, dz)); }
+                    best = fmaxf(best, s);
+                }
+            }
+        }
+        best = warp_reduce(best, OpMax());
+        if (lane == 0) atomicMax(&h.best_bits, __float_as_uint(best));
+        __syncthreads();
+        if (tid == 0) h.count = 0u;                    // nothing left for md_pairs
+        __syncthreads();
+    }
+    if (tid < (int)(sizeof(MdHeader) / 4)) reinterpret_cast<unsigned*>(gh)[tid] = reinterpret_cast<const unsigned*>(&h)[tid];
 }
 
 template <int DIM>
@@ -182,11 +310,15 @@ int launch_max_dist(const char* packed, int64_t n_src, float eps2, int64_t* scal
     float4* cand = reinterpret_cast<float4*>(reinterpret_cast<char*>(ws) + sizeof(MdHeader));
     int64_t blocks = (n_src + 255) / 256;
     if (blocks > kNumSMsB200 * 8) blocks = kNumSMsB200 * 8;
-    md_init<<<1, 32, 0, st>>>(h);
-    md_bbox<DIM><<<(int)blocks, 256, 0, st>>>(packed, n_src, h);
-    md_far_point<DIM><<<(int)blocks, 256, 0, st>>>(packed, n_src, h);
-    md_lower_bound<DIM><<<(int)blocks, 256, 0, st>>>(packed, n_src, h);
-    md_compact<DIM><<<(int)blocks, 256, 0, st>>>(packed, n_src, h, cand);
+    if (n_src <= kMdSmallMax) {
+        md_small<DIM><<<1, 1024, 0, st>>>(packed, n_src, h, cand);
+    } else {
+        md_init<<<1, 32, 0, st>>>(h);
+        md_bbox<DIM><<<(int)blocks, 256, 0, st>>>(packed, n_src, h);
+        md_far_point<DIM><<<(int)blocks, 256, 0, st>>>(packed, n_src, h);
+        md_lower_bound<DIM><<<(int)blocks, 256, 0, st>>>(packed, n_src, h);
+        md_compact<DIM><<<(int)blocks, 256, 0, st>>>(packed, n_src, h, cand);
+    }
     md_pairs<DIM><<<(int)blocks, 256, 0, st>>>(cand, h);
     md_publish<<<1, 32, 0, st>>>(h, eps2, scalars);
     NB_CUDA_LAUNCH_CHECK();

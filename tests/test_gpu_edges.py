@@ -159,13 +159,15 @@ def test_empty_and_tiny_tensors_in_free_quantisers():
 
 
 @pytest.mark.parametrize("dim", [2, 3])
-@pytest.mark.parametrize("shape", ["disk", "shell", "cluster_far", "line", "grid", "two", "one"])
+@pytest.mark.parametrize("shape", ["disk", "shell", "cluster_far", "line", "grid", "two", "one", "disk_large", "shell_large"])
 def test_pruned_max_dist_is_bit_exact(shape, dim):
     """nb_max_dist_sq (outer-shell candidates only) == brute-force max over all pairs of the reference's d²."""
     import nbody_cosmological_simulation_b200 as nb
     from nbody_cosmological_simulation_b200 import _lib as L
     g = torch.Generator().manual_seed(sum(map(ord, shape)) + dim)
-    n = {"two": 2, "one": 1}.get(shape, 3001)
+    # 3001 points take the single-CTA path (all phases in one launch), 40 001 the multi-launch one
+    n = {"two": 2, "one": 1, "disk_large": 40001, "shell_large": 40001}.get(shape, 3001)
+    shape = shape.replace("_large", "")
     if shape == "disk":
         pos = torch.randn(n, dim, generator=g) * 3.0
     elif shape == "shell":                      # every point is a candidate: worst case for the pruning
@@ -181,10 +183,10 @@ def test_pruned_max_dist_is_bit_exact(shape, dim):
         pos = torch.randn(n, dim, generator=g)
     eps_sq = 0.1 ** 2
     cpu = pos.float()
-    diff = cpu.unsqueeze(0) - cpu.unsqueeze(1)
     # simulation.py:83-86 evaluated by torch on the CPU — the oracle's rounding order ((dx²+dy²)+dz²); torch's CUDA
     # reduction adds the three squares in another order and can differ by an ulp
-    want = ((diff ** 2).sum(dim=-1) + eps_sq).max().item()
+    want = max((((cpu.unsqueeze(0) - cpu[r:r + 1000].unsqueeze(1)) ** 2).sum(dim=-1) + eps_sq).max().item()
+               for r in range(0, n, 1000))
     pos = cpu.to(DEV)
     lib = L.load()
     mass = torch.ones(n, device=DEV)
@@ -198,7 +200,7 @@ def test_pruned_max_dist_is_bit_exact(shape, dim):
     got = lib.nb_double_from_key(int(scal[0].item()))
     assert got == want, (shape, got, want)
     hdr = ws[:128].view(torch.int32)
-    count = int(hdr[7].item()) & 0xffffffff
+    count = int(hdr[9].item()) & 0xffffffff                                # candidates found
     assert 1 <= count <= n
     if shape in ("disk", "cluster_far", "line"):
         assert count < n // 4                                             # the pruning actually prunes
