@@ -342,6 +342,32 @@ def main():
                          "value": interactions_per_step / (f64_ms * 1e-3), "unit": UNIT,
                          "tflops_at_20_flop": FLOP_PER_INTERACTION * interactions_per_step / (f64_ms * 1e-3) / 1e12}
         del sim64
+        # the other precision modes of quantization.py at the benchmark's N and D (one force pass each; int modes include
+        # the max-d² pass and the level-table build), plus the potential-energy reduction of metrics/energy tracking
+        modes = {}
+        for mname in ("float16", "bfloat16", "int8_sim", "int4_sim"):
+            simm = nb.GalaxySimulation(pos.to(dev), vel.to(dev), mass.to(dev), precision_mode=nb.get_mode_from_string(mname),
+                                       G=G, softening=SOFTENING, dt=DT, device=dev)        # construction = one force pass (warm-up)
+            xm, _, mm = simm._state()
+            pkm = simm._pack(xm, mm)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            simm._accelerations_raw(xm, mm, pkm)
+            e1.record()
+            torch.cuda.synchronize()
+            m_ms = e0.elapsed_time(e1)
+            modes[mname] = {"ms_per_force_pass": m_ms, "value": interactions_per_step / (m_ms * 1e-3), "unit": UNIT}
+            if mname == "int4_sim":
+                simm._pe_cache = None
+                e0.record()
+                simm.get_potential_energy()
+                e1.record()
+                torch.cuda.synchronize()
+                extra["potential_energy"] = {"ms": e0.elapsed_time(e1), "unordered_pairs_per_s":
+                                             N_PARTICLES * (N_PARTICLES - 1) / 2 / (e0.elapsed_time(e1) * 1e-3),
+                                             "kernel": "potential_kernel (half-ring pair partition)"}
+            del simm
+        extra["modes"] = modes
 
     if rank == 0:
         peak_tf, peak_src = measured_fp32_peak()
@@ -376,6 +402,7 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": config_dict(world),
                 "tflops_at_20_flop": value * FLOP_PER_INTERACTION / 1e12,
                 "roofline": roofline, "roofline_kdk": extra.get("kdk"), "fp64": extra.get("fp64"),
+                "other_modes": extra.get("modes"), "potential_energy": extra.get("potential_energy"),
                 "cpu_baseline": cpu, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "note": "state uploaded from pinned host memory and downloaded again every step through "
