@@ -133,7 +133,7 @@ struct PotentialF64 {
 template <typename T, typename TM, int DIM, int IPT, int THREADS>
 __global__ void __launch_bounds__(THREADS + 32) potential_kernel(const char* __restrict__ src, int64_t n_chunks,
                                                                  const T* __restrict__ pos_tgt, const TM* __restrict__ mass_tgt,
-                                                                 int64_t n_tgt, int64_t tgt_offset, int triangular,
+                                                                 int64_t n_tgt, int64_t tgt_offset, int triangular,   /* targets are an index-aligned slice of the sources: half-ring partition */
                                                                  int chunks_per_split, double eps_sq,
                                                                  double* __restrict__ block_partials) {
     // Unordered pairs: out = Σ_{i<j} m_i m_j / r_ij.  With chunk-aligned targets (triangular != 0) a CTA streams the

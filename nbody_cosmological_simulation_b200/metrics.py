@@ -3,7 +3,7 @@
 On the hot path named by BASELINE.json: `compute_rotation_curve` — one radius-max reduction
 plus one binned sum/count kernel and two host reads instead of ~3·bins+1 synchronising masked reductions
 (metrics.py:48-78) — and `collect_metrics`, whose O(N²) potential energy goes through
-`GalaxySimulation.get_potential_energy` (upper-triangle pair kernel, cached per state).
+`GalaxySimulation.get_potential_energy` (half-ring pair kernel: every unordered pair once, cached per state).
 The O(N) remainder that SURVEY.md §8f ranks "next" is widened here too: `compute_galaxy_radius` is an exact radix
 select (no sort) and `compute_velocity_dispersion` a one-pass fp64 moment reduction; `compute_bound_fraction` needs
 the rank of every star in radius order and stays a device-side torch sort/cumsum.
