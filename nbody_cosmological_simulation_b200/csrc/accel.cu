@@ -27,6 +27,9 @@ namespace nb {
 #ifndef NB_LUTF_IPT
 #define NB_LUTF_IPT 2
 #endif
+#ifndef NB_LUTF_REDO_INLINE
+#define NB_LUTF_REDO_INLINE __noinline__
+#endif
 #ifndef NB_LUTF_THREADS
 #define NB_LUTF_THREADS 256
 #endif
@@ -69,6 +72,8 @@ struct ForceF32 {
     float lo2, scale, min_val;
     // Q_LUTF (lut.cuh): lane-replicated factor table g[k][lane] (an LDS.32 at k·128 + lane·4 never bank-conflicts
     // and moves 4× fewer shared-memory wavefronts than the 16-byte entries of Q_LUT), thresholds for the slow path
+    float nxs[IPT], nys[IPT], nzs[IPT];    // −x_i as scalars: packed ops take them in the broadcast form (one register, not a pair)
+    float scale_s, cm_s, eps_s;
     uint32_t lutg_lane;                    // shared-window address of g[0][lane]
     const float* thr_smem;                 // T_j, j = 0..P
     LutFast lf;
@@ -85,6 +90,7 @@ struct ForceF32 {
             if (i >= a.n_tgt) i = a.n_tgt - 1;
             const float x = pos[i * DIM + 0], y = pos[i * DIM + 1], z = DIM == 3 ? pos[i * DIM + 2] : 0.f;
             nx[t] = make_float2(-x, -x); ny[t] = make_float2(-y, -y); nz[t] = make_float2(-z, -z);
+            if (QMODE == Q_LUTF) { nxs[t] = -x; nys[t] = -y; nzs[t] = -z; }
             ax[t] = ay[t] = az[t] = make_float2(0.f, 0.f);
             sx[t] = sy[t] = sz[t] = 0.0;
         }
@@ -108,6 +114,7 @@ struct ForceF32 {
             clamp_lo = e < min_val;
             scale2 = make_float2(lf.scale, lf.scale);
             cm2 = make_float2(lf.cm, lf.cm);
+            scale_s = lf.scale; cm_s = lf.cm; eps_s = e;
             kmask = (uint32_t)(lf.p - 1) << kLutFb;
             n_levels = a.levels;
             lutg_lane = smem_u32(lut_smem) + 4u * (threadIdx.x & 31);
@@ -118,7 +125,7 @@ struct ForceF32 {
     // Q_LUTF: force factors of a source pair against one target.  Per scalar: MUFU.LG2, half an FFMA2, LOP3 + LEA.HI
     // (address), LDS.32, LOP3 (doubt predicate).
     __device__ __forceinline__ float2 lutf_lookup(float2 t, bool& doubt) const {
-        const float2 w = fma2(make_float2(lg2_approx(t.x), lg2_approx(t.y)), scale2, cm2);
+        const float2 w = fma2(make_float2(lg2_approx(t.x), lg2_approx(t.y)), make_float2(scale_s, scale_s), make_float2(cm_s, cm_s));
         const uint32_t wx = __float_as_uint(w.x), wy = __float_as_uint(w.y);
         doubt = doubt || ((wx & lf.zmask) == 0u) || ((wy & lf.zmask) == 0u);
         float2 g;
@@ -140,7 +147,7 @@ struct ForceF32 {
         return ge - gf;
     }
     template <bool FULL, bool CLAMP>
-    __device__ __noinline__ void lutf_redo(const unsigned char* s, int p) {
+    __device__ NB_LUTF_REDO_INLINE void lutf_redo(const unsigned char* s, int p) {
         const float4 a = reinterpret_cast<const float4*>(s)[p];
         const float2 xs = make_float2(a.x, a.y), ys = make_float2(a.z, a.w);
         float2 zs = make_float2(0.f, 0.f), ms;
@@ -233,10 +240,13 @@ struct ForceF32 {
             bool doubt = false;
 #pragma unroll
             for (int t = 0; t < IPT; ++t) {
-                const float2 dx = add2(xs, nx[t]), dy = add2(ys, ny[t]);
+                const float2 dx = add2(xs, make_float2(nxs[t], nxs[t])), dy = add2(ys, make_float2(nys[t], nys[t]));
                 float2 dz = make_float2(0.f, 0.f);
-                if (DIM == 3) dz = add2(zs, nz[t]);
-                float2 tq = dist_sq<true>(dx, dy, dz);   // fused d²: < 7 ulp from the exact-order value, inside the lookup margin (lut.cuh)
+                if (DIM == 3) dz = add2(zs, make_float2(nzs[t], nzs[t]));
+                const float2 e2 = make_float2(eps_s, eps_s);
+                float2 tq = fma2(dx, dx, e2);                // fused d²: < 7 ulp from the exact-order value, inside the lookup margin (lut.cuh)
+                tq = fma2(dy, dy, tq);
+                if (DIM == 3) tq = fma2(dz, dz, tq);   // fused d²: < 7 ulp from the exact-order value, inside the lookup margin (lut.cuh)
                 if (CLAMP) tq = make_float2(fmaxf(tq.x, min_val), fmaxf(tq.y, min_val));
                 const float2 w = mul2(lutf_lookup(tq, doubt), ms);
                 ax[t] = fma2(w, dx, ax[t]);
