@@ -137,9 +137,9 @@ int nb_lut_selfcheck(const int64_t* scalars, double eps_sq, double min_dist_sq, 
  * over all outputs is folded into scalars[NB_SLOT_ACC_MIN/MAX] (quantization.py:78-79) and the snap
  * itself is nb_snap_accelerations or fused into nb_kdk.
  * uniform_mass != 0 asserts that every real source has mass == mass_value (the caller has checked): the
- * fp32-state FLOAT32 / FLOAT16 / BFLOAT16 kernels and the fp64-state FLOAT64 kernel then drop the per-pair mass
- * multiply (12 -> 11 packed fp32 ops, 16 -> 15 fp64 ops per pair) and scale by G·mass_value once per target;
- * other modes ignore the hint. */
+ * fp32-state FLOAT32 / FLOAT16 / BFLOAT16 kernels, the fp64-state FLOAT64 kernel and the level-table kernel for
+ * levels <= 256 (INT8_SIM, INT4_SIM, CUSTOM) then drop the per-pair mass multiply (12 -> 11 packed fp32 ops,
+ * 16 -> 15 fp64 ops per pair) and scale by mass_value once per target; other combinations ignore the hint. */
 int nb_accel(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt, int dim,
              int dtype, int mode, double G, double eps_sq, const void* level_table, int levels,
              int uniform_mass, double mass_value,

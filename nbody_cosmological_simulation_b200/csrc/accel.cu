@@ -47,6 +47,7 @@ struct AccelArgs {
     int levels;
     int lut_rep;              // shared-memory replication of the level table (1, 2, 4 or 8 copies, see accel_kernel)
     float neg_zero;           // -0.0f, passed at run time so that the compiler cannot fold fma(d, d, -0) back into a mul
+    float uniform_mass;       // Q_LUTF: != 0 when every real source has this mass (the per-pair mass multiply is dropped)
 };
 
 // Level table layout (Q_LUT): float4 entry[k] = { T_{k+1}, g_k, g_{k+1}, 0 } for k = 0..L-1, preceded by a
@@ -81,6 +82,7 @@ struct ForceF32 {
     uint32_t kmask;                        // (P-1) << kLutFb: the level bits of W
     int n_levels;
     bool clamp_lo;                         // eps² < min_val: d² must be clamped from below (quantization.py:106)
+    float inv_uniform_mass;                // 1/m when all real sources have mass m (0: general masses)
 
     __device__ __forceinline__ void init(const AccelArgs& a, const float4* lut_smem) {
         const float* pos = reinterpret_cast<const float*>(a.pos_tgt);
@@ -112,6 +114,7 @@ struct ForceF32 {
             lf = lut_fast_load(tab, a.levels);
             min_val = tab[0].z;
             clamp_lo = e < min_val;
+            inv_uniform_mass = a.uniform_mass != 0.f ? 1.0f / a.uniform_mass : 0.f;
             scale2 = make_float2(lf.scale, lf.scale);
             cm2 = make_float2(lf.cm, lf.cm);
             scale_s = lf.scale; cm_s = lf.cm; eps_s = e;
@@ -146,7 +149,7 @@ struct ForceF32 {
         const float gf = lds_f32(lutg_lane + ((w & kmask) >> (kLutFb - 7)));
         return ge - gf;
     }
-    template <bool FULL, bool CLAMP>
+    template <bool FULL, bool CLAMP, bool MUL_MASS>
     __device__ NB_LUTF_REDO_INLINE void lutf_redo(const unsigned char* s, int p) {
         const float4 a = reinterpret_cast<const float4*>(s)[p];
         const float2 xs = make_float2(a.x, a.y), ys = make_float2(a.z, a.w);
@@ -155,7 +158,7 @@ struct ForceF32 {
         else ms = reinterpret_cast<const float2*>(s + kChunkABytes)[p];
         // massless records (the padding of the last chunk: 240 identical far-away points whose common W may well sit in
         // the doubt zone and then overflow every thread's queue) contribute exactly 0 whatever their level is
-        if (ms.x == 0.f && ms.y == 0.f) return;
+        if (MUL_MASS && ms.x == 0.f && ms.y == 0.f) return;
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
             const float2 dx = add2(xs, nx[t]), dy = add2(ys, ny[t]);
@@ -166,7 +169,8 @@ struct ForceF32 {
                 tq = make_float2(fmaxf(tq.x, min_val), fmaxf(tq.y, min_val));
                 tf = make_float2(fmaxf(tf.x, min_val), fmaxf(tf.y, min_val));
             }
-            const float2 w = mul2(make_float2(lutf_exact<FULL>(tq.x, tf.x), lutf_exact<FULL>(tq.y, tf.y)), ms);
+            float2 w = make_float2(lutf_exact<FULL>(tq.x, tf.x), lutf_exact<FULL>(tq.y, tf.y));
+            if (MUL_MASS) w = mul2(w, ms);
             ax[t] = fma2(w, dx, ax[t]);
             ay[t] = fma2(w, dy, ay[t]);
             if (DIM == 3) az[t] = fma2(w, dz, az[t]);
@@ -211,7 +215,17 @@ struct ForceF32 {
 
     __device__ __forceinline__ void chunk(const unsigned char* s, int64_t c) {
         if (QMODE == Q_LUTF) {
-            if (clamp_lo) chunk_lutf<true>(s); else chunk_lutf<false>(s);
+            // Uniform masses: the pair loop drops the mass multiply (the common mass is applied once per target in the
+            // reduction) — except in a chunk that ends with padding records (mass 0, always at the end of a chunk), which
+            // takes the multiplying loop and is rescaled by 1/m when its partial sums are flushed.
+            const float last_mass = DIM == 3 ? reinterpret_cast<const float4*>(s + kChunkABytes)[kChunkUnits - 1].w
+                                             : reinterpret_cast<const float2*>(s + kChunkABytes)[kChunkUnits - 1].y;
+            const bool plain = inv_uniform_mass != 0.f && last_mass != 0.f;
+            if (plain) { if (clamp_lo) chunk_lutf<true, false>(s, 1.f); else chunk_lutf<false, false>(s, 1.f); }
+            else {
+                const float rescale = inv_uniform_mass != 0.f ? inv_uniform_mass : 1.f;
+                if (clamp_lo) chunk_lutf<true, true>(s, rescale); else chunk_lutf<false, true>(s, rescale);
+            }
             return;
         }
         chunk_direct(s, c);
@@ -224,8 +238,8 @@ struct ForceF32 {
     // thread-chunks for ordinary tables (a 4-entry queue overflowed 1.6 times per launch at N = 10⁴ and the straggling
     // CTA doubled the kernel time); tables whose levels are denser than floats overflow always and redo every chunk
     // on the slow path.
-    template <bool CLAMP>
-    __device__ __forceinline__ void chunk_lutf(const unsigned char* s) {
+    template <bool CLAMP, bool MUL_MASS>
+    __device__ __forceinline__ void chunk_lutf(const unsigned char* s, float rescale) {
         const float4* A = reinterpret_cast<const float4*>(s);
         const float4* B4 = reinterpret_cast<const float4*>(s + kChunkABytes);
         const float2* B2 = reinterpret_cast<const float2*>(s + kChunkABytes);
@@ -248,7 +262,8 @@ struct ForceF32 {
                 tq = fma2(dy, dy, tq);
                 if (DIM == 3) tq = fma2(dz, dz, tq);   // fused d²: < 7 ulp from the exact-order value, inside the lookup margin (lut.cuh)
                 if (CLAMP) tq = make_float2(fmaxf(tq.x, min_val), fmaxf(tq.y, min_val));
-                const float2 w = mul2(lutf_lookup(tq, doubt), ms);
+                float2 w = lutf_lookup(tq, doubt);
+                if (MUL_MASS) w = mul2(w, ms);
                 ax[t] = fma2(w, dx, ax[t]);
                 ay[t] = fma2(w, dy, ay[t]);
                 if (DIM == 3) az[t] = fma2(w, dz, az[t]);
@@ -259,9 +274,17 @@ struct ForceF32 {
             if (queued > 8u) {
 #pragma unroll
                 for (int t = 0; t < IPT; ++t) ax[t] = ay[t] = az[t] = make_float2(0.f, 0.f);
-                for (int p = 0; p < kChunkUnits; ++p) lutf_redo<true, CLAMP>(s, p);
+                for (int p = 0; p < kChunkUnits; ++p) lutf_redo<true, CLAMP, MUL_MASS>(s, p);
             } else {
-                for (; queued; --queued, q0 = __funnelshift_r(q0, q1, 8), q1 >>= 8) lutf_redo<false, CLAMP>(s, (int)(q0 & 0xffu));
+                for (; queued; --queued, q0 = __funnelshift_r(q0, q1, 8), q1 >>= 8) lutf_redo<false, CLAMP, MUL_MASS>(s, (int)(q0 & 0xffu));
+            }
+        }
+        if (MUL_MASS && rescale != 1.f) {
+#pragma unroll
+            for (int t = 0; t < IPT; ++t) {
+                ax[t] = make_float2(ax[t].x * rescale, ax[t].y * rescale);
+                ay[t] = make_float2(ay[t].x * rescale, ay[t].y * rescale);
+                az[t] = make_float2(az[t].x * rescale, az[t].y * rescale);
             }
         }
         flush();
@@ -624,6 +647,7 @@ int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, 
     a.table = level_table;
     a.levels = levels;
     a.neg_zero = -0.0f;
+    a.uniform_mass = (lut && levels <= kLutFastMaxLevels && uniform_mass != 0 && mass_value != 0.0) ? (float)mass_value : 0.f;
 
     int splits = 0, rc = NB_ERR_INVALID_ARGUMENT;
     constexpr int TH = kForceThreads, IPT = kForceIPT;
@@ -665,7 +689,7 @@ int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, 
     out->partial = a.partial;
     out->splits = splits;
     out->count = n_tgt * dim;
-    out->scale = lut ? 1.0 : (uni ? G * mass_value : G);
+    out->scale = lut ? (a.uniform_mass != 0.f ? (double)a.uniform_mass : 1.0) : (uni ? G * mass_value : G);
     out->out_f64 = dtype == NB_F64 || mode == NB_MODE_FLOAT64;
     out->minmax = mode == NB_MODE_INT8_SIM || mode == NB_MODE_INT4_SIM;
     return NB_OK;

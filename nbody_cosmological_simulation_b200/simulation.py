@@ -26,7 +26,7 @@ from . import _lib as L
 from . import overrides
 from .quantization import PrecisionMode, levels_for_mode
 
-_UNIFORM_MASS_MODES = (PrecisionMode.FLOAT32, PrecisionMode.FLOAT64, PrecisionMode.FLOAT16, PrecisionMode.BFLOAT16)
+_UNIFORM_MASS_MODES = tuple(PrecisionMode)        # every mode has a uniform-mass kernel variant (the library ignores the hint otherwise)
 _INT_FORCE_SNAP = {PrecisionMode.INT8_SIM: 256, PrecisionMode.INT4_SIM: 16}      # simulation.py:115
 
 
