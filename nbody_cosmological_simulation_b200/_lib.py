@@ -136,8 +136,33 @@ def uniform_mass(m: torch.Tensor):
 
 
 def ptr(t):
-    return None if t is None else c_void_p(t.data_ptr())
+    """Device address of a tensor as a plain int (ctypes converts it for a c_void_p parameter); None stays NULL."""
+    return None if t is None else t.data_ptr()
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
 def stream_ptr(device=None):
-    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """cudaStream_t of torch's current stream on `device` (an int for a c_void_p parameter; 0 = the legacy default)."""
+    if _raw_stream is not None and device is not None and device.index is not None:
+        return _raw_stream(device.index) or None
+    return torch.cuda.current_stream(device).cuda_stream or None
+
+
+class on_device:
+    """`with on_device(dev):` — torch.cuda.device(dev) only when dev is not already current (the context manager
+    costs several microseconds per step() of a small system; the common single-GPU case needs no switch)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if device.index is None or device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False

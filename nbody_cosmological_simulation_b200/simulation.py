@@ -141,7 +141,7 @@ class GalaxySimulation:
         packed = buf.bytes(f"packed{code}", nbytes)
         key = self._packed_cache_key(x, m, packed)
         if getattr(self, "_packed_key", None) != key:
-            with torch.cuda.device(x.device):
+            with L.on_device(x.device):
                 L.check(L.load().nb_pack_sources(L.ptr(x), L.ptr(m), n, dim, code, L.dtype_code(m), L.ptr(packed), 0,
                                                  L.stream_ptr(x.device)), "nb_pack_sources")
             self._packed_key = key
@@ -187,7 +187,7 @@ class GalaxySimulation:
         eps_sq = float(self.softening_sq)
         table = None
         uni, m0 = L.uniform_mass(m) if mode in _UNIFORM_MASS_MODES else (False, 0.0)
-        with torch.cuda.device(x.device):
+        with L.on_device(x.device):
             st = L.stream_ptr(x.device)
             if levels:
                 L.check(lib.nb_reset_scalars(L.ptr(buf.scalars), st), "nb_reset_scalars")
@@ -208,7 +208,7 @@ class GalaxySimulation:
         packed = self._pack(x, m)
         acc, snap_levels = self._accelerations_raw(x, m, packed)
         if snap_levels:
-            with torch.cuda.device(x.device):
+            with L.on_device(x.device):
                 L.check(L.load().nb_snap_accelerations(L.ptr(acc), acc.numel(), L.dtype_code(acc), snap_levels,
                                                        L.ptr(self._buf().scalars), L.stream_ptr(x.device)),
                         "nb_snap_accelerations")
@@ -220,6 +220,9 @@ class GalaxySimulation:
     def _promoted_state(self, acc: torch.Tensor):
         """x, v, a in the dtype torch's promotion gives `v + a * scalar` (Appendix A: fp32 ⊕ fp64 → fp64)."""
         x, v, m = self._state()
+        dt = x.dtype
+        if v.dtype == dt and acc.dtype == dt and dt in (torch.float32, torch.float64):
+            return x, v, m, acc.contiguous()              # the steady state of every run: nothing to promote
         dt = torch.promote_types(torch.promote_types(x.dtype, v.dtype), acc.dtype)
         if dt not in (torch.float32, torch.float64):
             raise L.NbodyLibraryError(f"unsupported state dtype {dt}")
@@ -235,7 +238,7 @@ class GalaxySimulation:
         packed = None
         if emit_packed:
             packed = buf.bytes(f"packed{code}", lib.nb_packed_bytes(n, dim, code))
-        with torch.cuda.device(v.device):
+        with L.on_device(v.device):
             L.check(lib.nb_kdk(L.ptr(x) if drift else None, L.ptr(v), L.ptr(a), L.ptr(x_out), L.ptr(v_out), n, dim, code,
                                float(self.dt), phase, snap_levels, L.ptr(buf.scalars), L.ptr(m),
                                L.dtype_code(m), L.ptr(packed), 0, L.stream_ptr(v.device)), "nb_kdk")
@@ -296,7 +299,7 @@ class GalaxySimulation:
         table = buf.bytes("level_table", lib.nb_level_table_bytes(levels)) if levels else None
         ws = buf.bytes("accel_ws", max(lib.nb_accel_workspace_bytes(n, dim),
                                        lib.nb_max_dist_workspace_bytes(n) if levels else 0))
-        with torch.cuda.device(x.device):
+        with L.on_device(x.device):
             L.check(lib.nb_run_ticks(L.ptr(x_in), L.ptr(v_in), L.ptr(a_in), L.ptr(x), L.ptr(v), L.ptr(a), L.ptr(m), n, dim,
                                      code, L.dtype_code(m),
                                      L.MODE_CODES[mode.value], levels, snap_levels, float(self.G), float(self.softening_sq),
@@ -352,7 +355,7 @@ class GalaxySimulation:
         n, dim = v.shape
         out = torch.empty(1, dtype=torch.float64, device=v.device)
         ws = buf.bytes("energy_ws", lib.nb_energy_workspace_bytes(n))
-        with torch.cuda.device(v.device):
+        with L.on_device(v.device):
             L.check(lib.nb_kinetic_energy(L.ptr(v), L.ptr(m), n, dim, L.dtype_code(v), L.dtype_code(m), L.ptr(out),
                                           L.ptr(ws), ws.numel(), L.stream_ptr(v.device)), "nb_kinetic_energy")
         return out, torch.promote_types(v.dtype, m.dtype)
@@ -387,7 +390,7 @@ class GalaxySimulation:
         packed = self._pack(x, m)
         out = torch.empty(1, dtype=torch.float64, device=x.device)
         ws = buf.bytes("energy_ws", lib.nb_energy_workspace_bytes(n))
-        with torch.cuda.device(x.device):
+        with L.on_device(x.device):
             L.check(lib.nb_potential_energy(L.ptr(packed), n, L.ptr(x), L.ptr(m), n, 0, dim, L.dtype_code(x),
                                             L.dtype_code(m), float(self.softening_sq), L.ptr(out), L.ptr(ws),
                                             ws.numel(), L.stream_ptr(x.device)), "nb_potential_energy")
