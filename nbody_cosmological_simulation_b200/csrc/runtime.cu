@@ -94,7 +94,9 @@ extern "C" int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_
     }
     for (; remaining > 0; --remaining)
         if ((rc = enqueue_tick(a, /*first=*/false, deferred, &ps, st))) return rc;
-    if (deferred && (rc = accel_reduce(ps, acc, scalars, st))) return rc;
-    // closing half kick (with the force snap of INT8/INT4) so that the state is observable
+    // closing half kick (with the force snap of INT8/INT4) so that the state is observable; in the deferred case the
+    // same kernel reduces the last force pass's partial sums and writes `acc`
+    if (deferred)
+        return kdk_from_partials(nullptr, v, acc, nullptr, v, n, dim, dtype, dt, NB_KDK_KICK, scalars, mass, mass_dtype, nullptr, 0, ps, st);
     return nb_kdk(nullptr, v, acc, nullptr, v, n, dim, dtype, dt, NB_KDK_KICK, snap_levels, scalars, mass, mass_dtype, nullptr, 0, st);
 }
