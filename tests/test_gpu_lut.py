@@ -64,3 +64,26 @@ def test_int_modes_with_uniform_and_general_masses(mode, masses, n):
     err = np.linalg.norm(got.cpu().double().numpy() - want.double().numpy(), axis=1) / np.linalg.norm(want.double().numpy(), axis=1)
     # identical levels except where a CPU-vs-CUDA logf ulp flips a pair on a boundary (tests/test_gpu_parity.py)
     assert np.median(err) <= 2e-6 and (err <= 1e-5).mean() >= 0.9 and err.max() <= 2e-3
+
+
+@pytest.mark.parametrize("mode,dim", [("int8_sim", 2), ("int4_sim", 3)])
+def test_int_mode_forces_are_pairwise_antisymmetric_at_scale(mode, dim):
+    """Size-independent property at N = 262 144: the level of a pair depends on d² only, so the pre-snap forces obey
+    Newton's third law pair by pair and Σ_i m_i a_i vanishes up to rounding — through the fast lookup, the doubt queue
+    and the slow-path corrections alike (a pair resolved differently in its two orders would show up here)."""
+    import nbody_cosmological_simulation_b200 as nb
+    from oracle import reference_port as ora
+    n = 262144
+    if dim == 2:
+        torch.manual_seed(12)
+        pos, vel, mass = nb.create_disk_galaxy(n, device=torch.device("cpu"))
+    else:
+        pos, vel, mass = ora.uniform_box(n, seed=9, dim=3)
+    mass = mass * (1.0 + 0.5 * (torch.arange(n) % 3 == 0).to(mass.dtype))              # general masses
+    sim = nb.GalaxySimulation(pos.to(DEV), vel.to(DEV), mass.to(DEV), precision_mode=nb.get_mode_from_string(mode))
+    x, _, m = sim._state()
+    a, _ = sim._accelerations_raw(x, m, sim._pack(x, m))
+    ma = (m.double().unsqueeze(1) * a.double())
+    net = ma.sum(dim=0).norm().item()
+    scale = ma.norm(dim=1).sum().item()
+    assert net <= 2e-6 * scale, (net, scale)
