@@ -40,6 +40,7 @@ def main():
     ap.add_argument("config", choices=["c4", "c5"])
     ap.add_argument("--stars", type=int, default=None)
     ap.add_argument("--ticks", type=int, default=None)
+    ap.add_argument("--modes", default="int8_sim,int4_sim", help="c5: comma-separated precision modes")
     ap.add_argument("--no-rescale", action="store_true",
                     help="c4: keep G=1e-3 and unit masses (the reference's defaults are tuned for N~5000: at N=4M the disk is "
                          "far out of equilibrium for dt=0.01 and the energy moves by tens of percent)")
@@ -76,7 +77,7 @@ def main():
     else:
         ticks = args.ticks or 1
         pos, vel, mass = pos.float(), vel.float(), mass.float()
-        for mode in ("int8_sim", "int4_sim"):
+        for mode in args.modes.split(","):
             sim, t_init = timed(lambda: ShardedGalaxySimulation(pos, vel, mass, precision_mode=nb.get_mode_from_string(mode)), dev, world)
             _, ms = timed(lambda: sim.run(ticks), dev, world)
             distinct = torch.unique(sim.accelerations).numel()
