@@ -10,7 +10,8 @@
     nb_accel                               tiled O(N²) pair loop, sources streamed by TMA bulk copies
     nb_kdk(KICK)                           only when the state must be observable (end of step()/callback)
 
-with every scalar that the reference pulls to the host (`if max - min < 1e-10`) kept on the device.
+(inside nb_run_ticks the reduction of the pair kernel's j-split partial sums rides on the following kick kernel, so
+a steady-state tick of a float mode is two launches), with every scalar that the reference pulls to the host (`if max - min < 1e-10`) kept on the device.
 The arithmetic contract (which ops are separately rounded, dtype promotion, reduction tolerances) is
 SURVEY.md Appendix A.  There is no CPU path: CPU tensors raise.
 """
