@@ -29,7 +29,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define NB_ABI_VERSION 1
+#define NB_ABI_VERSION 2
 
 typedef enum NbStatus {
     NB_OK = 0,
@@ -145,6 +145,27 @@ int nb_accel(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t
              int uniform_mass, double mass_value,
              void* acc_out, int64_t* scalars, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* nb_accel for FLOAT32 mode on fp32 state / FLOAT64 mode on fp64 state that ALSO returns the potential energy of the
+ * same configuration: acc_out as nb_accel, pe_out[0] (device double) = ½ Σ_i m_i Σ_{j≠i} m_j / r_ij over the n_tgt
+ * targets (an i-range shard adds its ranks; caller applies −G) — simulation.py:176-192 folded into the force pass
+ * (get_total_energy() every tick, crash_point_test.py:190-197).  The targets must be among the sources (their j == i
+ * term, d² == ε² exactly, is removed analytically).  mass_tgt: (n_tgt,) of mass_dtype. */
+int nb_accel_potential(const void* packed_src, int64_t n_src, const void* pos_tgt, const void* mass_tgt, int64_t n_tgt,
+                       int dim, int dtype, int mass_dtype, int mode, double G, double eps_sq, int uniform_mass,
+                       double mass_value, void* acc_out, double* pe_out, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+
+/* Instrumentation: record the CUDA events `start_event` / `stop_event` (cudaEvent_t as void*) immediately before and
+ * after the NEXT pair-kernel launch issued by this host thread (inside nb_accel, nb_accel_potential or nb_run_ticks),
+ * on that launch's stream; one-shot.  bench.py times the dominant kernel with it without leaving the default path. */
+int nb_profile_next_force(void* start_event, void* stop_event);
+/* Plain cudaEvent_t helpers for the hook above (so that a caller needs no CUDA runtime binding of its own):
+ * create (timing enabled), elapsed milliseconds (synchronises on stop_event — host-blocking, instrumentation only),
+ * destroy. */
+int nb_event_create(void** event_out);
+int nb_event_elapsed_ms(void* start_event, void* stop_event, float* ms_out);
+int nb_event_destroy(void* event);
+
 /* quantize_force -> _grid_quantize(a, levels) (simulation.py:115-116, quantization.py:74-88) with the
  * global min/max taken from scalars[NB_SLOT_ACC_MIN/MAX]; in place on acc (n*dim values, acc_dtype). */
 int nb_snap_accelerations(void* acc, int64_t count, int acc_dtype, int levels, const int64_t* scalars,
@@ -173,12 +194,18 @@ int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_o
  * to issuing those calls one by one.  levels = d² grid levels (0 for float modes), snap_levels = force grid levels
  * (INT8/INT4, else 0).  use_graph != 0 captures the tick body once into a CUDA graph and replays it (worth it for
  * small systems where launch latency dominates).  packed: nb_packed_bytes; level_table: nb_level_table_bytes (or
- * NULL); workspace: max(nb_accel_workspace_bytes, nb_max_dist_workspace_bytes) — the two uses never overlap. */
+ * NULL); workspace: max(nb_accel_workspace_bytes, nb_max_dist_workspace_bytes) — the two uses never overlap.
+ * pe_out (device double[1], may be NULL): when given, the force pass of the LAST tick also accumulates Σ_j m_j / r_ij
+ * per target (one more packed op per source pair) and pe_out[0] receives Σ_{i<j} m_i m_j / r_ij of the final
+ * positions — nb_potential_energy's value without its second O(N²) pass (simulation.py:176-192; caller applies −G).
+ * Only where the pair loop sees the unquantised d² in the state dtype: fp32 state in FLOAT32 mode, fp64 state in
+ * FLOAT64 mode; NB_ERR_UNSUPPORTED otherwise. */
 int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_in, void* x, void* v, void* acc,
                  const void* mass, int64_t n, int dim, int dtype, int mass_dtype,
                  int mode, int levels, int snap_levels, double G, double eps_sq, double min_dist_sq, double dt,
                  int64_t ticks, int uniform_mass, double mass_value, void* packed, void* level_table,
-                 int64_t* scalars, void* workspace, int64_t workspace_bytes, int use_graph, void* stream);
+                 int64_t* scalars, void* workspace, int64_t workspace_bytes, int use_graph, double* pe_out,
+                 void* stream);
 
 /* ---- energies: simulation.py:170-196 ------------------------------------------------------- */
 int64_t nb_energy_workspace_bytes(int64_t n_targets);

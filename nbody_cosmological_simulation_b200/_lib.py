@@ -22,7 +22,7 @@ MODE_CODES = {"float64": 0, "float32": 1, "bfloat16": 2, "float16": 3, "int8_sim
 KDK_KICK_DRIFT, KDK_KICK, KDK_KICK_KICK_DRIFT = 0, 1, 2
 SLOT_MAX_D2, SLOT_ACC_MIN, SLOT_ACC_MAX, SLOT_VAL_MIN, SLOT_VAL_MAX, SLOT_RADIUS_MAX = 0, 1, 2, 3, 4, 5
 SCALAR_SLOTS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _P = c_void_p
 # name -> (restype, argtypes); must list every symbol include/nbody_b200.h declares
@@ -48,7 +48,13 @@ PROTOTYPES = {
     "nb_snap_accelerations": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     "nb_kdk": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_double, c_int, c_int, _P, _P, c_int, _P, c_int64, _P]),
     "nb_run_ticks": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
-                             c_double, c_int64, c_int, c_double, _P, _P, _P, _P, c_int64, c_int, _P]),
+                             c_double, c_int64, c_int, c_double, _P, _P, _P, _P, c_int64, c_int, _P, _P]),
+    "nb_accel_potential": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_double, c_double, c_int, c_double,
+                                   _P, _P, _P, c_int64, _P]),
+    "nb_profile_next_force": (c_int, [_P, _P]),
+    "nb_event_create": (c_int, [POINTER(c_void_p)]),
+    "nb_event_elapsed_ms": (c_int, [_P, _P, POINTER(ctypes.c_float)]),
+    "nb_event_destroy": (c_int, [_P]),
     "nb_energy_workspace_bytes": (c_int64, [c_int64]),
     "nb_potential_energy": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_double, _P, _P, c_int64, _P]),
     "nb_kinetic_energy": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, _P, c_int64, _P]),
@@ -123,7 +129,7 @@ def uniform_mass(m: torch.Tensor):
     cached.  The entry holds a weak reference to the tensor: the caching allocator recycles addresses, so a key made
     of data_ptr alone would serve a dead tensor's answer to a new tensor that landed on the same address."""
     key = (m.data_ptr(), m._version, m.numel(), m.dtype)
-    hit = _uniform_cache.get(key)
+    hit = None if os.environ.get("NB_B200_NO_CACHE", "0") == "1" else _uniform_cache.get(key)
     if hit is not None and hit[0]() is m:
         return hit[1]
     if len(_uniform_cache) > 64:
@@ -133,6 +139,41 @@ def uniform_mass(m: torch.Tensor):
     value = (lo == hi, float(lo))
     _uniform_cache[key] = (weakref.ref(m), value)
     return value
+
+
+def forget_uniform_mass(m: torch.Tensor) -> None:
+    _uniform_cache.pop((m.data_ptr(), m._version, m.numel(), m.dtype), None)
+
+
+class ForceTimer:
+    """CUDA events around the pair-kernel launches of the calls that follow `arm()` (nb_profile_next_force): the way
+    bench.py times the dominant kernel inside the default step()/run() path.  Instrumentation only."""
+
+    def __init__(self):
+        self.lib = load()
+        self.pairs = []
+
+    def arm(self):
+        e0, e1 = c_void_p(), c_void_p()
+        check(self.lib.nb_event_create(ctypes.byref(e0)), "nb_event_create")
+        check(self.lib.nb_event_create(ctypes.byref(e1)), "nb_event_create")
+        check(self.lib.nb_profile_next_force(e0, e1), "nb_profile_next_force")
+        self.pairs.append((e0, e1))
+
+    def disarm(self):
+        check(self.lib.nb_profile_next_force(None, None), "nb_profile_next_force")
+
+    def times_ms(self):
+        """Durations of the armed launches (synchronises); events are released."""
+        out = []
+        for e0, e1 in self.pairs:
+            ms = ctypes.c_float()
+            check(self.lib.nb_event_elapsed_ms(e0, e1, ctypes.byref(ms)), "nb_event_elapsed_ms")
+            out.append(ms.value)
+            self.lib.nb_event_destroy(e0)
+            self.lib.nb_event_destroy(e1)
+        self.pairs = []
+        return out
 
 
 def ptr(t):

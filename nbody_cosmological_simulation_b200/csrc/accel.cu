@@ -42,6 +42,7 @@ struct AccelArgs {
     int64_t n_tgt;
     int chunks_per_split;
     double* partial;          // [splits][n_tgt][DIM]
+    double* partial_phi;      // PHI variants: [splits][n_tgt] sums of m_j / r_ij (the potential at each target), else unused
     double eps_sq;
     const void* table;        // level table (Q_LUT)
     int levels;
@@ -59,14 +60,21 @@ struct AccelArgs {
 // ======================================================================================================
 // UNI: all source masses are equal (checked by the caller): the per-pair `·m_j` is dropped and the common mass is
 // applied once per target in the finalize pass; padding records then rely on their far-away position (w == 0).
-template <int DIM_, int QMODE, int IPT, int THREADS_, bool UNI = false, int UNROLL = 4>
+// PHI (Q_F32 only): the pair loop also accumulates Σ_j m_j / r_ij per target — r = rsqrt(d²) is already in a register,
+// so the potential costs ONE more packed op per source pair (FFMA2; FADD2 with uniform masses) instead of a second
+// O(N²) pass (simulation.py:176-192 evaluated on the state the force pass has just seen).
+template <int DIM_, int QMODE, int IPT, int THREADS_, bool UNI = false, int UNROLL = 4, bool PHI = false>
 struct ForceF32 {
     static constexpr int DIM = DIM_;
     static constexpr int THREADS = THREADS_;
     static constexpr int TARGETS_PER_THREAD = IPT;
+    static constexpr bool HAS_PHI = PHI;
+    static_assert(!PHI || QMODE == Q_F32, "the potential is defined on the unquantised d² (simulation.py:181-186)");
     float2 nx[IPT], ny[IPT], nz[IPT];      // {-x_i, -x_i}: targets, negated and duplicated for packed adds
     float2 ax[IPT], ay[IPT], az[IPT];      // chunk-local sums; .x = even sources, .y = odd sources
     double sx[IPT], sy[IPT], sz[IPT];      // running fp64 sums
+    float2 ap[IPT];                        // PHI: chunk-local Σ m_j / r_ij
+    double sp[IPT];
     float2 eps2;
     float neg_zero;
     const float4* lut;                     // shared-memory copy of the level table (Q_LUT)
@@ -95,6 +103,7 @@ struct ForceF32 {
             if (QMODE == Q_LUTF) { nxs[t] = -x; nys[t] = -y; nzs[t] = -z; }
             ax[t] = ay[t] = az[t] = make_float2(0.f, 0.f);
             sx[t] = sy[t] = sz[t] = 0.0;
+            if (PHI) { ap[t] = make_float2(0.f, 0.f); sp[t] = 0.0; }
         }
         const float e = (float)a.eps_sq;                // softening_sq cast to the tensor dtype (simulation.py:86)
         eps2 = make_float2(e, e);
@@ -228,7 +237,27 @@ struct ForceF32 {
             }
             return;
         }
-        chunk_direct(s, c);
+        if (!UNI && QMODE != Q_LUT) {
+            // General masses, but THIS chunk's 256 sources may still share one mass (mass classes laid out in blocks:
+            // jitter_test.py:45-86 nested levels, reality_glitch_tests.py:366-397 wall galaxy): then the pair loop is the
+            // uniform-mass one (11 packed ops instead of 12) and the common mass scales the chunk's flush.  Decided per
+            // warp from shared memory (4 LDS + a vote per 128 iterations); chunks that end in padding stay general.
+            const int lane = threadIdx.x & 31;
+            float m_first, eq = 1.f;
+            if (DIM == 3) {
+                const float4* B = reinterpret_cast<const float4*>(s + kChunkABytes);
+                m_first = B[0].z;
+#pragma unroll
+                for (int q = 0; q < kChunkUnits / 32; ++q) { const float4 b = B[lane + 32 * q]; if (b.z != m_first || b.w != m_first) eq = 0.f; }
+            } else {
+                const float2* B = reinterpret_cast<const float2*>(s + kChunkABytes);
+                m_first = B[0].x;
+#pragma unroll
+                for (int q = 0; q < kChunkUnits / 32; ++q) { const float2 b = B[lane + 32 * q]; if (b.x != m_first || b.y != m_first) eq = 0.f; }
+            }
+            if (__all_sync(0xffffffffu, eq != 0.f) && m_first != 0.f) { chunk_direct<true>(s, m_first); return; }
+        }
+        chunk_direct<UNI>(s, 1.f);
     }
 
     // Main loop without a branch: every iteration (one source pair x IPT targets) takes the fast lookup; an iteration
@@ -290,17 +319,23 @@ struct ForceF32 {
         flush();
     }
 
-    __device__ __forceinline__ void flush() {
+    // `scale`: common mass of a chunk that ran the uniform-mass loop inside a general-mass launch (else 1)
+    __device__ __forceinline__ void flush(float scale = 1.f) {
         // flush the chunk-local fp32 sums into the fp64 accumulators
+        const double sc = (double)scale;
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
-            sx[t] += (double)(ax[t].x + ax[t].y); ax[t] = make_float2(0.f, 0.f);
-            sy[t] += (double)(ay[t].x + ay[t].y); ay[t] = make_float2(0.f, 0.f);
-            if (DIM == 3) { sz[t] += (double)(az[t].x + az[t].y); az[t] = make_float2(0.f, 0.f); }
+            sx[t] = fma((double)(ax[t].x + ax[t].y), sc, sx[t]); ax[t] = make_float2(0.f, 0.f);
+            sy[t] = fma((double)(ay[t].x + ay[t].y), sc, sy[t]); ay[t] = make_float2(0.f, 0.f);
+            if (DIM == 3) { sz[t] = fma((double)(az[t].x + az[t].y), sc, sz[t]); az[t] = make_float2(0.f, 0.f); }
+            if (PHI) { sp[t] = fma((double)(ap[t].x + ap[t].y), sc, sp[t]); ap[t] = make_float2(0.f, 0.f); }
         }
     }
 
-    __device__ __forceinline__ void chunk_direct(const unsigned char* s, int64_t) {
+    // ULOOP: every source of this chunk has the same mass — it is left out of the pair loop (applied by the caller's
+    // finalize pass when the whole launch is uniform (UNI), by flush(chunk_mass) otherwise)
+    template <bool ULOOP>
+    __device__ __forceinline__ void chunk_direct(const unsigned char* s, float chunk_mass) {
         const float4* A = reinterpret_cast<const float4*>(s);
         const float4* B4 = reinterpret_cast<const float4*>(s + kChunkABytes);
         const float2* B2 = reinterpret_cast<const float2*>(s + kChunkABytes);
@@ -330,8 +365,9 @@ struct ForceF32 {
                         d2 = __bfloat1622float2(h);
                     }
                     const float2 r = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
-                    if (UNI) w = mul2(mul2(r, r), r);           // 1 / d²^1.5 (common mass applied in finalize)
+                    if (ULOOP) w = mul2(mul2(r, r), r);         // 1 / d²^1.5 (common mass applied at the flush / in finalize)
                     else w = mul2(mul2(r, r), mul2(r, ms));     // m_j / d²^1.5             simulation.py:97-105
+                    if (PHI) ap[t] = ULOOP ? add2(r, ap[t]) : fma2(ms, r, ap[t]);    // Σ_j m_j / r_ij   simulation.py:185-188
                 }
                 // Σ_j w·diff (simulation.py:112).  Register-bank note (tools/regbank.cu): an FFMA2 with three distinct
                 // register pairs issues in 3 cycles, not 2 (two banks, one 64-lane read each per cycle), so this loop's
@@ -342,7 +378,7 @@ struct ForceF32 {
                 if (DIM == 3) az[t] = fma2(w, dz, az[t]);
             }
         }
-        flush();
+        flush(chunk_mass);
     }
 
     __device__ __forceinline__ void store(const AccelArgs& a) const {
@@ -353,6 +389,7 @@ struct ForceF32 {
             if (i < a.n_tgt) {
                 out[i * DIM + 0] = sx[t]; out[i * DIM + 1] = sy[t];
                 if (DIM == 3) out[i * DIM + 2] = sz[t];
+                if (PHI) a.partial_phi[(int64_t)blockIdx.y * a.n_tgt + i] = sp[t];
             }
         }
     }
@@ -383,13 +420,17 @@ __device__ __forceinline__ double inv_dist_cubed(double d2) {     // mass_over_d
     return fma(w, ce, w);
 }
 
-template <int DIM_, int QMODE, int IPT, int THREADS_, bool UNI = false, int UNROLL = 2>
+// PHI (Q_F64 only): Σ_j m_j / r_ij from the same pass — 1/r = d² · d²^(-3/2), one more DFMA per pair.
+template <int DIM_, int QMODE, int IPT, int THREADS_, bool UNI = false, int UNROLL = 2, bool PHI = false>
 struct ForceF64 {
     static constexpr int DIM = DIM_;
     static constexpr int THREADS = THREADS_;
     static constexpr int TARGETS_PER_THREAD = IPT;
+    static constexpr bool HAS_PHI = PHI;
+    static_assert(!PHI || QMODE == Q_F64, "the potential is defined on the unquantised d² (simulation.py:181-186)");
     double xi[IPT], yi[IPT], zi[IPT];
     double sx[IPT], sy[IPT], sz[IPT];
+    double sp[IPT];
     double eps2;
 
     __device__ __forceinline__ void init(const AccelArgs& a, const float4*) {
@@ -400,10 +441,46 @@ struct ForceF64 {
             if (i >= a.n_tgt) i = a.n_tgt - 1;
             xi[t] = pos[i * DIM + 0]; yi[t] = pos[i * DIM + 1]; zi[t] = DIM == 3 ? pos[i * DIM + 2] : 0.0;
             sx[t] = sy[t] = sz[t] = 0.0;
+            if (PHI) sp[t] = 0.0;
         }
         eps2 = a.eps_sq;
     }
     __device__ __forceinline__ void chunk(const unsigned char* s, int64_t) {
+        if (!UNI && QMODE == Q_F64) {
+            // general masses, but this chunk's 128 sources may share one mass: uniform-mass loop (15 ops instead of 16)
+            // into chunk-local sums, scaled by the common mass when they are added to the running sums (see ForceF32)
+            const int lane = threadIdx.x & 31;
+            double m_first;
+            bool eq = true;
+            if (DIM == 3) {
+                const double2* B = reinterpret_cast<const double2*>(s + kChunkABytes);
+                m_first = B[0].y;
+#pragma unroll
+                for (int q = 0; q < kChunkUnits / 32; ++q) eq = eq && B[lane + 32 * q].y == m_first;
+            } else {
+                const double* B = reinterpret_cast<const double*>(s + kChunkABytes);
+                m_first = B[0];
+#pragma unroll
+                for (int q = 0; q < kChunkUnits / 32; ++q) eq = eq && B[lane + 32 * q] == m_first;
+            }
+            if (__all_sync(0xffffffffu, eq) && m_first != 0.0) {
+                double lx[IPT], ly[IPT], lz[IPT], lp[IPT];
+#pragma unroll
+                for (int t = 0; t < IPT; ++t) lx[t] = ly[t] = lz[t] = lp[t] = 0.0;
+                pair_loop<true>(s, lx, ly, lz, lp);
+#pragma unroll
+                for (int t = 0; t < IPT; ++t) {
+                    sx[t] = fma(lx[t], m_first, sx[t]); sy[t] = fma(ly[t], m_first, sy[t]);
+                    if (DIM == 3) sz[t] = fma(lz[t], m_first, sz[t]);
+                    if (PHI) sp[t] = fma(lp[t], m_first, sp[t]);
+                }
+                return;
+            }
+        }
+        pair_loop<UNI>(s, sx, sy, sz, sp);
+    }
+    template <bool ULOOP>
+    __device__ __forceinline__ void pair_loop(const unsigned char* s, double (&ox)[IPT], double (&oy)[IPT], double (&oz)[IPT], double (&op)[IPT]) {
         const double2* A = reinterpret_cast<const double2*>(s);
         const double2* B2 = reinterpret_cast<const double2*>(s + kChunkABytes);
         const double* B1 = reinterpret_cast<const double*>(s + kChunkABytes);
@@ -420,7 +497,8 @@ struct ForceF64 {
                 if (DIM == 3) d2 = fma(dz, dz, d2);
                 double w;
                 if (QMODE == Q_F64) {
-                    w = UNI ? inv_dist_cubed(d2) : mass_over_dist_cubed(d2, m);
+                    w = ULOOP ? inv_dist_cubed(d2) : mass_over_dist_cubed(d2, m);
+                    if (PHI) op[t] = fma(d2, w, op[t]);                           // [m_j] · d² · d²^(-3/2) = [m_j] / r_ij
                 } else {
                     float u = (float)d2;                                         // dist_sq.float()
                     if (QMODE == Q_F16) u = __half2float(__float2half_rn(u));
@@ -428,9 +506,9 @@ struct ForceF64 {
                     const float r = rsqrt_approx(u);
                     w = (double)((r * r) * (r * (float)m));
                 }
-                sx[t] = fma(w, dx, sx[t]);
-                sy[t] = fma(w, dy, sy[t]);
-                if (DIM == 3) sz[t] = fma(w, dz, sz[t]);
+                ox[t] = fma(w, dx, ox[t]);
+                oy[t] = fma(w, dy, oy[t]);
+                if (DIM == 3) oz[t] = fma(w, dz, oz[t]);
             }
         }
     }
@@ -442,6 +520,7 @@ struct ForceF64 {
             if (i < a.n_tgt) {
                 out[i * DIM + 0] = sx[t]; out[i * DIM + 1] = sy[t];
                 if (DIM == 3) out[i * DIM + 2] = sz[t];
+                if (PHI) a.partial_phi[(int64_t)blockIdx.y * a.n_tgt + i] = sp[t];
             }
         }
     }
@@ -449,6 +528,7 @@ struct ForceF64 {
 
 template <int DIM_, int IPT, int THREADS_>
 struct ForceMixed {       // fp32 sources/targets, FLOAT64 mode
+    static constexpr bool HAS_PHI = false;
     static constexpr int DIM = DIM_;
     static constexpr int THREADS = THREADS_;
     static constexpr int TARGETS_PER_THREAD = IPT;
@@ -515,7 +595,7 @@ constexpr int kMaxLevelsSmem = 4096;      // level table entries staged in share
 
 // LUTKIND: 0 = no level table, 1 = 16-byte entries replicated per bank group (Q_LUT), 2 = fast lookup (Q_LUTF)
 template <class Consumer, int LUTKIND>
-__global__ void __launch_bounds__(Consumer::THREADS + 32, LUTKIND == 2 ? NB_LUTF_MINB : 0) accel_kernel(const AccelArgs a) {
+__global__ void __launch_bounds__(Consumer::THREADS + 32, LUTKIND == 2 ? NB_LUTF_MINB : (Consumer::HAS_PHI ? 3 : 0)) accel_kernel(const AccelArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const bool is_consumer = threadIdx.x < Consumer::THREADS;
     const float4* lut_smem = nullptr;
@@ -579,16 +659,55 @@ __global__ void __launch_bounds__(256) accel_finalize_kernel(const double* __res
     }
 }
 
+// Potential energy from the per-target potentials a PHI force pass left behind:
+//   out[0] = Σ_{i<j} m_i m_j / r_ij = ½ Σ_i m_i (φ_i − self_i),   φ_i = phi_scale · Σ_splits partial_phi[s][i],
+// where self_i is the j == i term of the pair loop (d² == ε² exactly), removed by subtracting the identical expression.
+template <typename T, typename TM>
+__global__ void __launch_bounds__(256) phi_energy_kernel(const double* __restrict__ partial_phi, int splits, int64_t n_tgt,
+                                                         double phi_scale, bool uniform, const TM* __restrict__ mass, double eps_sq,
+                                                         double* __restrict__ block_partials) {
+    __shared__ double red[32];
+    double self_unit;                      // 1 / r of the self pair as the pair loop evaluates it
+    if constexpr (sizeof(T) == 4) self_unit = (double)rsqrt_approx((float)eps_sq);
+    else self_unit = eps_sq * inv_dist_cubed(eps_sq);
+    double mine = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_tgt; i += (int64_t)gridDim.x * blockDim.x) {
+        double phi = 0.0;
+        for (int sp = 0; sp < splits; ++sp) phi += partial_phi[(int64_t)sp * n_tgt + i];
+        const double m = (double)mass[i];
+        // uniform masses: the loop summed 1/r and phi_scale is the common mass; general: it summed m_j / r
+        const double self = uniform ? self_unit : m * self_unit;
+        mine = fma(m, (phi - self) * phi_scale, mine);
+    }
+    const double tot = block_reduce(mine, OpAdd(), 0.0, red);
+    if (threadIdx.x == 0) block_partials[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(1024) phi_final_kernel(const double* __restrict__ partials, int count, double* __restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int e = threadIdx.x; e < count; e += blockDim.x) s += partials[e];
+    s = block_reduce(s, OpAdd(), 0.0, red);
+    if (threadIdx.x == 0) out[0] = 0.5 * s;
+}
+
 // ---- host side -----------------------------------------------------------------------------------------
 constexpr int kForceThreads = 256;
 constexpr int kForceIPT = 2;
 constexpr int kTargetsPerBlock = kForceThreads * kForceIPT;
 
+constexpr int64_t kPhiBlockBytes = 16 * 1024;        // per-CTA partial sums of the potential reduction (phi_energy_kernel)
+
+// Instrumentation hook (nb_profile_next_force): CUDA events recorded around the NEXT pair-kernel launch of this host
+// thread, then forgotten.  bench.py uses it to time the dominant kernel inside nb_run_ticks without changing the path.
+struct ForceProfile { void* start; void* stop; };
+inline ForceProfile& force_profile() { static thread_local ForceProfile p{nullptr, nullptr}; return p; }
+
 template <class Consumer, int LUTKIND>
-int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, int* splits_out) {
+int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, int* splits_out, double** phi_out = nullptr) {
     AccelArgs a = a0;
-    const int64_t per_split = a.n_tgt * Consumer::DIM * (int64_t)sizeof(double);
-    int64_t max_by_ws = workspace_bytes / per_split;
+    // a PHI consumer keeps one more double per target and split (the potential), behind the acceleration partials
+    const int64_t per_split = a.n_tgt * (Consumer::DIM + (Consumer::HAS_PHI ? 1 : 0)) * (int64_t)sizeof(double);
+    int64_t max_by_ws = (workspace_bytes - (Consumer::HAS_PHI ? kPhiBlockBytes : 0)) / per_split;
     if (max_by_ws < 1) return NB_ERR_WORKSPACE_TOO_SMALL;
     const int cap = max_splits_for(a.n_tgt, Consumer::DIM);
     if (max_by_ws > cap) max_by_ws = cap;
@@ -608,9 +727,15 @@ int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, 
     if (frc != NB_OK) return frc;
     const SplitPlan p = plan_splits(a.n_tgt, a.n_chunks, Consumer::THREADS * Consumer::TARGETS_PER_THREAD, ctas_per_sm, (int)max_by_ws);
     a.chunks_per_split = p.chunks_per_split;
+    if (Consumer::HAS_PHI) a.partial_phi = a.partial + (int64_t)p.splits * a.n_tgt * Consumer::DIM;
+    ForceProfile& prof = force_profile();
+    if (prof.start) cudaEventRecord((cudaEvent_t)prof.start, st);
     kern<<<dim3(p.blocks_i, p.splits), Consumer::THREADS + 32, smem, st>>>(a);
     NB_CUDA_LAUNCH_CHECK();
+    if (prof.stop) cudaEventRecord((cudaEvent_t)prof.stop, st);
+    prof.start = prof.stop = nullptr;                     // one-shot
     *splits_out = p.splits;
+    if (phi_out) *phi_out = a.partial_phi;
     return NB_OK;
 }
 
@@ -621,13 +746,14 @@ using namespace nb;
 #ifndef NB_TUNE_HARNESS
 extern "C" int64_t nb_accel_workspace_bytes(int64_t n_targets, int dim) {
     if (n_targets <= 0 || (dim != 2 && dim != 3)) return 0;
-    // room for the largest j-split the planner may choose for this many targets
-    return (int64_t)max_splits_for(n_targets, dim) * n_targets * dim * (int64_t)sizeof(double);
+    // room for the largest j-split the planner may choose for this many targets (+ one potential per target and split
+    // and the block partials of its reduction, for a pass that also returns the potential energy)
+    return (int64_t)max_splits_for(n_targets, dim) * n_targets * (dim + 1) * (int64_t)sizeof(double) + kPhiBlockBytes;
 }
 
 int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt, int dim, int dtype, int mode,
                     double G, double eps_sq, const void* level_table, int levels, int uniform_mass, double mass_value,
-                    int64_t* scalars, void* workspace, int64_t workspace_bytes, cudaStream_t st, PartialSums* out) {
+                    int64_t* scalars, void* workspace, int64_t workspace_bytes, cudaStream_t st, PartialSums* out, bool want_phi) {
     if (!packed_src || !pos_tgt || !workspace || n_src <= 0 || n_tgt <= 0 || (dim != 2 && dim != 3))
         return NB_ERR_INVALID_ARGUMENT;
     if (dtype != NB_F32 && dtype != NB_F64) return NB_ERR_INVALID_ARGUMENT;
@@ -636,6 +762,9 @@ int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, 
     if (lut && (!level_table || levels < 2 || !scalars)) return NB_ERR_INVALID_ARGUMENT;
     if (lut && levels > kMaxLevelsSmem) return NB_ERR_UNSUPPORTED;
     if (lut && dtype == NB_F64) return NB_ERR_UNSUPPORTED;       // fp64 state + int modes: no caller in the reference
+    // the fused potential exists where the pair loop sees the unquantised d² in the state dtype (simulation.py:181-186)
+    if (want_phi && !((dtype == NB_F32 && mode == NB_MODE_FLOAT32) || (dtype == NB_F64 && mode == NB_MODE_FLOAT64)))
+        return NB_ERR_UNSUPPORTED;
 
     AccelArgs a{};
     a.src = (const char*)packed_src;
@@ -650,6 +779,7 @@ int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, 
     a.uniform_mass = (lut && levels <= kLutFastMaxLevels && uniform_mass != 0 && mass_value != 0.0) ? (float)mass_value : 0.f;
 
     int splits = 0, rc = NB_ERR_INVALID_ARGUMENT;
+    double* phi = nullptr;
     constexpr int TH = kForceThreads, IPT = kForceIPT;
     // uniform-mass fast path: fp32 state in FLOAT32 / FLOAT16 / BFLOAT16 mode, fp64 state in FLOAT64 mode
     const bool uni = uniform_mass != 0 && ((dtype == NB_F32 && (mode == NB_MODE_FLOAT32 || mode == NB_MODE_FLOAT16 || mode == NB_MODE_BFLOAT16)) ||
@@ -657,6 +787,17 @@ int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, 
 #define NB_F32_UNI_CASE(D, Q) rc = launch_accel<ForceF32<D, Q, IPT, TH, true>, 0>(a, workspace_bytes, st, &splits)
 #define NB_F32_CASE(D, Q, LUT) rc = launch_accel<ForceF32<D, Q, IPT, TH>, LUT>(a, workspace_bytes, st, &splits)
 #define NB_F64_CASE(D, Q) rc = launch_accel<ForceF64<D, Q, IPT, TH>, 0>(a, workspace_bytes, st, &splits)
+#define NB_PHI_CASE(F, D, Q, U, UNR) rc = launch_accel<F<D, Q, IPT, TH, U, UNR, true>, 0>(a, workspace_bytes, st, &splits, &phi)
+    if (want_phi) {
+        if (dtype == NB_F32) {
+            if (uni) { if (dim == 2) NB_PHI_CASE(ForceF32, 2, Q_F32, true, 4); else NB_PHI_CASE(ForceF32, 3, Q_F32, true, 4); }
+            else { if (dim == 2) NB_PHI_CASE(ForceF32, 2, Q_F32, false, 4); else NB_PHI_CASE(ForceF32, 3, Q_F32, false, 4); }
+        } else {
+            if (uni) { if (dim == 2) NB_PHI_CASE(ForceF64, 2, Q_F64, true, 2); else NB_PHI_CASE(ForceF64, 3, Q_F64, true, 2); }
+            else { if (dim == 2) NB_PHI_CASE(ForceF64, 2, Q_F64, false, 2); else NB_PHI_CASE(ForceF64, 3, Q_F64, false, 2); }
+        }
+    } else
+#undef NB_PHI_CASE
     if (dtype == NB_F32) {
         if (mode == NB_MODE_FLOAT64) {
             if (dim == 2) rc = launch_accel<ForceMixed<2, IPT, TH>, 0>(a, workspace_bytes, st, &splits);
@@ -692,6 +833,39 @@ int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, 
     out->scale = lut ? (a.uniform_mass != 0.f ? (double)a.uniform_mass : 1.0) : (uni ? G * mass_value : G);
     out->out_f64 = dtype == NB_F64 || mode == NB_MODE_FLOAT64;
     out->minmax = mode == NB_MODE_INT8_SIM || mode == NB_MODE_INT4_SIM;
+    out->partial_phi = phi;
+    out->phi_scale = uni ? mass_value : 1.0;
+    out->phi_uniform = uni;
+    out->n_tgt = n_tgt;
+    return NB_OK;
+}
+
+int nb::potential_from_phi(const PartialSums& p, int dtype, const void* mass_tgt, int mass_dtype, double eps_sq, double* out,
+                           cudaStream_t st) {
+    if (!p.partial_phi || !mass_tgt || !out) return NB_ERR_INVALID_ARGUMENT;
+    // block partials live behind the potentials (launch_accel reserved kPhiBlockBytes there)
+    double* blocks = const_cast<double*>(p.partial_phi) + (int64_t)p.splits * p.n_tgt;
+    int64_t nb = (p.n_tgt + 255) / 256;
+    const int64_t cap = kPhiBlockBytes / (int64_t)sizeof(double);
+    if (nb > cap) nb = cap;
+    if (nb > kNumSMsB200 * 8) nb = kNumSMsB200 * 8;
+#define NB_PHI_E(T, TM) phi_energy_kernel<T, TM><<<(int)nb, 256, 0, st>>>(p.partial_phi, p.splits, p.n_tgt, p.phi_scale, p.phi_uniform, (const TM*)mass_tgt, eps_sq, blocks)
+    if (dtype == NB_F32 && mass_dtype == NB_F32) NB_PHI_E(float, float);
+    else if (dtype == NB_F32 && mass_dtype == NB_F64) NB_PHI_E(float, double);
+    else if (dtype == NB_F64 && mass_dtype == NB_F32) NB_PHI_E(double, float);
+    else if (dtype == NB_F64 && mass_dtype == NB_F64) NB_PHI_E(double, double);
+    else return NB_ERR_INVALID_ARGUMENT;
+#undef NB_PHI_E
+    NB_CUDA_LAUNCH_CHECK();
+    phi_final_kernel<<<1, 1024, 0, st>>>(blocks, (int)nb, out);
+    NB_CUDA_LAUNCH_CHECK();
+    return NB_OK;
+}
+
+extern "C" int nb_profile_next_force(void* start_event, void* stop_event) {
+    ForceProfile& p = force_profile();
+    p.start = start_event;
+    p.stop = stop_event;
     return NB_OK;
 }
 
@@ -713,8 +887,21 @@ extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_t
     if (!acc_out) return NB_ERR_INVALID_ARGUMENT;
     PartialSums p{};
     const int rc = accel_pairs(packed_src, n_src, pos_tgt, n_tgt, dim, dtype, mode, G, eps_sq, level_table, levels, uniform_mass,
-                               mass_value, scalars, workspace, workspace_bytes, (cudaStream_t)stream, &p);
+                               mass_value, scalars, workspace, workspace_bytes, (cudaStream_t)stream, &p, false);
     if (rc != NB_OK) return rc;
     return accel_reduce(p, acc_out, scalars, (cudaStream_t)stream);
+}
+
+extern "C" int nb_accel_potential(const void* packed_src, int64_t n_src, const void* pos_tgt, const void* mass_tgt, int64_t n_tgt,
+                                  int dim, int dtype, int mass_dtype, int mode, double G, double eps_sq, int uniform_mass,
+                                  double mass_value, void* acc_out, double* pe_out, void* workspace, int64_t workspace_bytes,
+                                  void* stream) {
+    if (!acc_out || !pe_out || !mass_tgt) return NB_ERR_INVALID_ARGUMENT;
+    PartialSums p{};
+    int rc = accel_pairs(packed_src, n_src, pos_tgt, n_tgt, dim, dtype, mode, G, eps_sq, nullptr, 0, uniform_mass, mass_value,
+                         nullptr, workspace, workspace_bytes, (cudaStream_t)stream, &p, true);
+    if (rc != NB_OK) return rc;
+    if ((rc = potential_from_phi(p, dtype, mass_tgt, mass_dtype, eps_sq, pe_out, (cudaStream_t)stream))) return rc;
+    return accel_reduce(p, acc_out, nullptr, (cudaStream_t)stream);
 }
 #endif  // NB_TUNE_HARNESS

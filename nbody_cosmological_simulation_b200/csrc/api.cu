@@ -47,3 +47,19 @@ extern "C" int64_t nb_num_chunks(int64_t n, int dtype) {
     return (cs == 0 || n <= 0) ? 0 : (n + cs - 1) / cs;
 }
 extern "C" int64_t nb_packed_bytes(int64_t n, int dim, int dtype) { return nb_num_chunks(n, dtype) * nb_chunk_bytes(dim, dtype); }
+
+// ---- instrumentation events (used with nb_profile_next_force) -------------------------------------------------
+extern "C" int nb_event_create(void** event_out) {
+    if (!event_out) return NB_ERR_INVALID_ARGUMENT;
+    cudaEvent_t e = nullptr;
+    const cudaError_t rc = cudaEventCreate(&e);
+    *event_out = (void*)e;
+    return cuda_status(rc);
+}
+extern "C" int nb_event_destroy(void* event) { return event ? cuda_status(cudaEventDestroy((cudaEvent_t)event)) : NB_OK; }
+extern "C" int nb_event_elapsed_ms(void* start_event, void* stop_event, float* ms_out) {
+    if (!start_event || !stop_event || !ms_out) return NB_ERR_INVALID_ARGUMENT;
+    cudaError_t rc = cudaEventSynchronize((cudaEvent_t)stop_event);
+    if (rc == cudaSuccess) rc = cudaEventElapsedTime(ms_out, (cudaEvent_t)start_event, (cudaEvent_t)stop_event);
+    return cuda_status(rc);
+}

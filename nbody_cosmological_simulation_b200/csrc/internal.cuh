@@ -14,11 +14,19 @@ struct PartialSums {
     double scale;            // G, G·m (uniform masses) or 1 (level-table factors carry G)
     bool out_f64;            // accelerations are fp64 (fp64 state or FLOAT64 mode)
     bool minmax;             // INT8/INT4: min/max of the outputs feed the force snap
+    const double* partial_phi;   // [splits][n_tgt] per-target potentials Σ_j m_j / r_ij (PHI pass), else NULL
+    double phi_scale;        // common mass (uniform-mass pass summed 1/r), else 1
+    bool phi_uniform;
+    int64_t n_tgt;
 };
 
 int accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt, int dim, int dtype, int mode,
                 double G, double eps_sq, const void* level_table, int levels, int uniform_mass, double mass_value,
-                int64_t* scalars, void* workspace, int64_t workspace_bytes, cudaStream_t st, PartialSums* out);
+                int64_t* scalars, void* workspace, int64_t workspace_bytes, cudaStream_t st, PartialSums* out,
+                bool want_phi = false);
+// out[0] = Σ_{i<j} m_i m_j / r_ij (this shard's targets against all sources) from the potentials of a PHI pass
+int potential_from_phi(const PartialSums& p, int dtype, const void* mass_tgt, int mass_dtype, double eps_sq, double* out,
+                       cudaStream_t st);
 int accel_reduce(const PartialSums& p, void* acc_out, int64_t* scalars, cudaStream_t st);
 
 // nb_kdk with the accelerations taken from j-split partial sums (reduced on the fly, written to `acc` as well)

@@ -22,7 +22,9 @@ struct TickArgs {
 // one tick body: [closing kick of the previous tick +] opening kick + drift (+ packed emit), then the force.
 // Float modes (`deferred`): the pair kernel leaves partial sums in the workspace; their reduction is folded into
 // the next tick's kick kernel (or done by finish_tick after the last one) — bit-identical to reducing first.
-int enqueue_tick(const TickArgs& a, bool first, bool deferred, PartialSums* ps, cudaStream_t st) {
+// `pe_out` != NULL (last tick of a call only): the force pass also accumulates the per-target potentials and the
+// potential energy of the NEW positions is left in pe_out[0] (one more packed op per pair instead of a second O(N²) pass).
+int enqueue_tick(const TickArgs& a, bool first, bool deferred, PartialSums* ps, cudaStream_t st, double* pe_out = nullptr) {
     const int phase = first ? NB_KDK_KICK_DRIFT : NB_KDK_KICK_KICK_DRIFT;
     int rc;
     if (deferred && !first)
@@ -40,7 +42,8 @@ int enqueue_tick(const TickArgs& a, bool first, bool deferred, PartialSums* ps, 
     }
     PartialSums now{};
     if ((rc = accel_pairs(a.packed, a.n, a.x, a.n, a.dim, a.dtype, a.mode, a.G, a.eps_sq, a.table, a.levels, a.uniform, a.mass_value,
-                          a.scalars, a.ws, a.ws_bytes, st, &now))) return rc;
+                          a.scalars, a.ws, a.ws_bytes, st, &now, pe_out != nullptr))) return rc;
+    if (pe_out && (rc = potential_from_phi(now, a.dtype, a.mass, a.mass_dtype, a.eps_sq, pe_out, st))) return rc;
     if (deferred) {
         // the plan (split count, scale) is a pure function of the arguments: every tick produces the same descriptor,
         // which is what lets a captured tick body be replayed
@@ -55,7 +58,7 @@ int enqueue_tick(const TickArgs& a, bool first, bool deferred, PartialSums* ps, 
 extern "C" int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_in, void* x, void* v, void* acc, const void* mass, int64_t n, int dim, int dtype, int mass_dtype, int mode,
                             int levels, int snap_levels, double G, double eps_sq, double min_dist_sq, double dt, int64_t ticks,
                             int uniform_mass, double mass_value, void* packed, void* level_table, int64_t* scalars,
-                            void* workspace, int64_t workspace_bytes, int use_graph, void* stream) {
+                            void* workspace, int64_t workspace_bytes, int use_graph, double* pe_out, void* stream) {
     if (!x || !v || !acc || !mass || !packed || !scalars || !workspace || n <= 0 || ticks < 0) return NB_ERR_INVALID_ARGUMENT;
     if (ticks == 0) return NB_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -66,11 +69,14 @@ extern "C" int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_
     // snap) and the accelerations have the state's dtype
     const bool acc_f64 = dtype == NB_F64 || mode == NB_MODE_FLOAT64;
     const bool deferred = snap_levels == 0 && acc_f64 == (dtype == NB_F64);
+    if (pe_out && !((dtype == NB_F32 && mode == NB_MODE_FLOAT32) || (dtype == NB_F64 && mode == NB_MODE_FLOAT64)))
+        return NB_ERR_UNSUPPORTED;                          // the fused potential needs the unquantised d² in the state dtype
     PartialSums ps{};
-    int rc = enqueue_tick(a, /*first=*/true, deferred, &ps, st);
+    int rc = enqueue_tick(a, /*first=*/true, deferred, &ps, st, ticks == 1 ? pe_out : nullptr);
     if (rc) return rc;
     int64_t remaining = ticks - 1;
-    if (use_graph && remaining >= 4) {
+    const int64_t tail = pe_out ? 1 : 0;                    // the last tick is enqueued directly when it carries the potential
+    if (use_graph && remaining - tail >= 4) {
         // capture one steady-state tick on a private stream (the caller's may be the legacy default stream, which
         // cannot be captured), then replay it on the caller's stream
         cudaStream_t cap = nullptr;
@@ -84,7 +90,7 @@ extern "C" int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_
             if (rc == NB_OK && e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
         }
         if (rc == NB_OK && e == cudaSuccess) {
-            for (; remaining > 0 && e == cudaSuccess; --remaining) e = cudaGraphLaunch(exec, st);
+            for (; remaining > tail && e == cudaSuccess; --remaining) e = cudaGraphLaunch(exec, st);
         }
         if (exec) cudaGraphExecDestroy(exec);          // deferred until the in-flight launches finish
         if (graph) cudaGraphDestroy(graph);
@@ -93,7 +99,7 @@ extern "C" int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_
         if (e != cudaSuccess) { cudaGetLastError(); return cuda_status(e); }
     }
     for (; remaining > 0; --remaining)
-        if ((rc = enqueue_tick(a, /*first=*/false, deferred, &ps, st))) return rc;
+        if ((rc = enqueue_tick(a, /*first=*/false, deferred, &ps, st, remaining == 1 ? pe_out : nullptr))) return rc;
     // closing half kick (with the force snap of INT8/INT4) so that the state is observable; in the deferred case the
     // same kernel reduces the last force pass's partial sums and writes `acc`
     if (deferred)

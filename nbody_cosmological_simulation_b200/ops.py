@@ -98,6 +98,22 @@ class CudaOps:
                                       ws.numel(), L.stream_ptr(x_tgt.device)), "nb_accel")
         return acc
 
+    def accel_potential(self, packed, n_src, x_tgt, m_tgt, mode: str, G, eps_sq, uniform=(False, 0.0)):
+        """accel() for FLOAT32-on-fp32 / FLOAT64-on-fp64 that also returns this shard's part of Σ_{i<j} m_i m_j / r_ij
+        (1-element fp64 device tensor) from the same pass (nb_accel_potential)."""
+        L.require_cuda(packed, x_tgt, m_tgt)
+        n, dim = x_tgt.shape
+        code = L.dtype_code(x_tgt)
+        acc = torch.empty((n, dim), dtype=x_tgt.dtype, device=x_tgt.device)
+        pe = torch.empty(1, dtype=torch.float64, device=x_tgt.device)
+        ws = self._scratch("accel", self.lib.nb_accel_workspace_bytes(n, dim), x_tgt.device)
+        with torch.cuda.device(x_tgt.device):
+            L.check(self.lib.nb_accel_potential(L.ptr(packed), int(n_src), L.ptr(x_tgt), L.ptr(m_tgt), n, dim, code,
+                                                L.dtype_code(m_tgt), L.MODE_CODES[mode], float(G), float(eps_sq),
+                                                int(bool(uniform[0])), float(uniform[1]), L.ptr(acc), L.ptr(pe), L.ptr(ws),
+                                                ws.numel(), L.stream_ptr(x_tgt.device)), "nb_accel_potential")
+        return acc, pe
+
     def snap(self, acc, levels, scalars):
         L.require_cuda(acc, scalars)
         with torch.cuda.device(acc.device):

@@ -19,6 +19,7 @@ import ast
 import inspect
 import os
 import textwrap
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -161,30 +162,38 @@ def recognise_source(source: str) -> Optional[OverrideSpec]:
     return _match_body(fn.body)
 
 
-_CACHE: dict = {}
+_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()     # function object -> spec (dies with the function)
+
+
+def _globals_ok(fn) -> bool:
+    """The names the canonical body uses must be bound to THIS package's quantiser and to torch."""
+    from . import quantization
+    g = fn.__globals__
+    return g.get("_grid_quantize_safe") is quantization._grid_quantize_safe and g.get("torch") is torch
 
 
 def recognise(cls, stock_function) -> Optional[OverrideSpec]:
-    """Spec for `cls._compute_accelerations` if it is a recognised override (cached per function object)."""
+    """Spec for `cls._compute_accelerations` if it is a recognised override.  Cached per function object in a
+    weak dictionary (the scripts define their subclass inside a function called once per level count,
+    sensitivity_test.py:55 — the entry goes when the class does); the two global bindings are re-checked on every
+    hit, so rebinding `_grid_quantize_safe` or `torch` in the script's module drops back to running the body as written."""
     fn = getattr(cls, "_compute_accelerations", None)
     fn = getattr(fn, "__func__", fn)
-    if fn in _CACHE:                      # per-tick fast path (the environment switch is read once per function)
-        return _CACHE[fn]
     if fn is None or fn is stock_function or not inspect.isfunction(fn):
         return None
-    if os.environ.get("NB_B200_RECOGNISE_OVERRIDES", "1") == "0":
-        _CACHE[fn] = None
-        return None
-    spec = None
     try:
-        # the names the body uses must be bound to THIS package's quantiser and to torch, and the body must not
-        # close over anything (a closure could rebind them)
-        from . import quantization
-        g = fn.__globals__
-        if g.get("_grid_quantize_safe") is quantization._grid_quantize_safe and g.get("torch") is torch \
-                and not fn.__code__.co_freevars:
-            spec = recognise_source(inspect.getsource(fn))
-    except (OSError, TypeError):
-        spec = None
+        spec = _CACHE[fn]
+    except KeyError:
+        pass
+    else:
+        return spec if spec is not None and _globals_ok(fn) else None
+    spec = None
+    if os.environ.get("NB_B200_RECOGNISE_OVERRIDES", "1") != "0":
+        try:
+            # the body must not close over anything (a closure could rebind the names it uses)
+            if _globals_ok(fn) and not fn.__code__.co_freevars:
+                spec = recognise_source(inspect.getsource(fn))
+        except (OSError, TypeError):
+            spec = None
     _CACHE[fn] = spec
     return spec

@@ -125,8 +125,10 @@ class ShardedGalaxySimulation:
             setattr(self, key, buf)
         return buf
 
-    def _force(self, x: torch.Tensor, emit: bool, local_packed: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Pre-snap accelerations of the local targets; `emit` packs x first (otherwise the KDK kernel already did)."""
+    def _force(self, x: torch.Tensor, emit: bool, local_packed: Optional[torch.Tensor] = None,
+               want_pe: bool = False) -> torch.Tensor:
+        """Pre-snap accelerations of the local targets; `emit` packs x first (otherwise the KDK kernel already did).
+        `want_pe`: the same pass also leaves this rank's share of the potential energy of `x` on the device."""
         ops, plan = self.ops, self._plan_for(x.dtype)
         if emit:
             local_packed = self._local_packed_buffer(x.dtype)
@@ -142,12 +144,23 @@ class ShardedGalaxySimulation:
             ops.max_dist_sq(packed, n_src, x, self.softening_sq, self.scalars)
             self._all_reduce(self.scalars[L.SLOT_MAX_D2:L.SLOT_MAX_D2 + 1], dist.ReduceOp.MAX)
             table = ops.build_level_table(self.scalars, x.dtype, self.softening_sq, 0.01, self.G, levels)
+        self._pe_local = None
+        if want_pe and self._pe_fusable(x):
+            acc, pe = ops.accel_potential(packed, n_src, x, self.masses, mode.value, self.G, self.softening_sq,
+                                          uniform=self._uniform_mass())
+            self._pe_local = (pe, x)                         # valid while `positions` is this tensor
+            return acc
         acc = ops.accel(packed, n_src, x, mode.value, self.G, self.softening_sq, table, levels, self.scalars,
                         uniform=self._uniform_mass())
         if mode in _INT_FORCE_SNAP:
             self._all_reduce(self.scalars[L.SLOT_ACC_MIN:L.SLOT_ACC_MIN + 1], dist.ReduceOp.MIN)
             self._all_reduce(self.scalars[L.SLOT_ACC_MAX:L.SLOT_ACC_MAX + 1], dist.ReduceOp.MAX)
         return acc
+
+    def _pe_fusable(self, x) -> bool:
+        mode = self.precision_mode
+        return (mode == PrecisionMode.FLOAT32 and x.dtype == torch.float32) or \
+               (mode == PrecisionMode.FLOAT64 and x.dtype == torch.float64)
 
     def _uniform_mass(self):
         """(all masses equal on every rank, value): local min/max, all-reduced; cached per masses tensor version."""
@@ -175,13 +188,14 @@ class ShardedGalaxySimulation:
         ops = self.ops
         x, v, a = self._promote()
         snap_levels, pending = 0, False
-        for _ in range(ticks):
+        want_pe, self._pe_wanted = getattr(self, "_pe_wanted", False), False
+        for t in range(ticks):
             phase = L.KDK_KICK_KICK_DRIFT if pending else L.KDK_KICK_DRIFT
             plan = self._plan_for(x.dtype)
             local_packed = self._local_packed_buffer(x.dtype)
             x, v = ops.kdk(phase, x, v, a, self.masses, self.dt, snap_levels if pending else 0, self.scalars,
                            packed=local_packed, total_chunks=plan.slot_chunks)
-            a = self._force(x, emit=False, local_packed=local_packed)
+            a = self._force(x, emit=False, local_packed=local_packed, want_pe=want_pe and t == ticks - 1)
             snap_levels = _INT_FORCE_SNAP.get(self.precision_mode, 0)
             pending = True
             self.tick += 1
@@ -219,6 +233,13 @@ class ShardedGalaxySimulation:
         return float(np.float32(val)) if self.velocities.dtype == torch.float32 else float(val)
 
     def get_potential_energy(self) -> float:
+        self._pe_wanted = True                  # the next span's last force pass carries the potential (simulation.py)
+        fused = getattr(self, "_pe_local", None)
+        if fused is not None and fused[1] is self.positions:
+            s = fused[0].clone()
+            self._all_reduce(s, dist.ReduceOp.SUM)
+            val = -float(self.G) * s.item()
+            return float(np.float32(val)) if self.positions.dtype == torch.float32 else float(val)
         x = self.positions.contiguous()
         packed, n_src = self._sources_for(x)
         plan = self._plan_for(x.dtype)

@@ -17,6 +17,7 @@ SURVEY.md Appendix A.  There is no CPU path: CPU tensors raise.
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Callable, Optional
 
@@ -29,6 +30,12 @@ from .quantization import PrecisionMode, levels_for_mode
 
 _UNIFORM_MASS_MODES = tuple(PrecisionMode)        # every mode has a uniform-mass kernel variant (the library ignores the hint otherwise)
 _INT_FORCE_SNAP = {PrecisionMode.INT8_SIM: 256, PrecisionMode.INT4_SIM: 16}      # simulation.py:115
+# The packed-source / potential-energy / uniform-mass caches validate on tensor identity + Tensor._version.  Writes
+# that bypass the version counter (x.data[...] = ..., DLPack / __cuda_array_interface__ consumers, foreign kernels
+# writing through data_ptr) are invisible to them: call sim.invalidate_caches() after such a write, or set
+# NB_B200_NO_CACHE=1 to disable the caches altogether.
+_NO_CACHE = os.environ.get("NB_B200_NO_CACHE", "0") == "1"
+_FUSE_PE = os.environ.get("NB_B200_FUSE_PE", "1") != "0" and not _NO_CACHE     # potential energy from the force pass
 
 
 class _DeviceBuffers:
@@ -45,6 +52,17 @@ class _DeviceBuffers:
             buf = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.device)
             self._bytes[key] = buf
         return buf
+
+
+class _DeferredPE:
+    """Σ_{i<j} m_i m_j / r_ij left in device memory by a potential-carrying force pass (nb_run_ticks pe_out)."""
+    __slots__ = ("dev", "G", "dtype")
+
+    def __init__(self, dev, G, dtype):
+        self.dev, self.G, self.dtype = dev, G, dtype
+
+    def read(self, as_float):
+        return as_float(-self.G * self.dev.item(), self.dtype)
 
 
 class GalaxySimulation:
@@ -97,6 +115,10 @@ class GalaxySimulation:
 
     @staticmethod
     def _is_stock(obj, name: str) -> bool:
+        """True when `obj.<name>` resolves to GalaxySimulation's own method: neither a subclass override nor an
+        instance-level patch (`sim.step = ...`, `sim._compute_accelerations = MethodType(f, sim)`)."""
+        if name in getattr(obj, "__dict__", ()):
+            return False
         return getattr(type(obj), name) is getattr(GalaxySimulation, name)
 
     MAX_GRID_LEVELS = 4096                 # level tables up to this size fit the force kernel's shared memory
@@ -109,6 +131,8 @@ class GalaxySimulation:
         if self._is_stock(self, "_compute_accelerations"):
             mode = self.precision_mode
             return mode, levels_for_mode(mode) or 0, 0.01, _INT_FORCE_SNAP.get(mode, 0)
+        if "_compute_accelerations" in self.__dict__:
+            return None                    # instance-level patch: arbitrary user code, runs as written
         spec = overrides.recognise(type(self), GalaxySimulation._compute_accelerations)
         if spec is None:
             return None
@@ -141,12 +165,19 @@ class GalaxySimulation:
         nbytes = L.load().nb_packed_bytes(n, dim, code)
         packed = buf.bytes(f"packed{code}", nbytes)
         key = self._packed_cache_key(x, m, packed)
-        if getattr(self, "_packed_key", None) != key:
+        if _NO_CACHE or getattr(self, "_packed_key", None) != key:
             with L.on_device(x.device):
                 L.check(L.load().nb_pack_sources(L.ptr(x), L.ptr(m), n, dim, code, L.dtype_code(m), L.ptr(packed), 0,
                                                  L.stream_ptr(x.device)), "nb_pack_sources")
             self._packed_key = key
         return packed
+
+    def invalidate_caches(self) -> None:
+        """Forget everything derived from the current positions / masses (packed sources, cached potential energy,
+        uniform-mass verdict).  Needed only after writes that bypass torch's version counter."""
+        self._packed_key = None
+        self._pe_cache = None
+        L.forget_uniform_mass(self.masses)
 
     class _PackedKey:
         """Identity of the (x, m) a packed buffer was built from.  Weak references pin the tensor OBJECTS: an address
@@ -300,35 +331,51 @@ class GalaxySimulation:
         table = buf.bytes("level_table", lib.nb_level_table_bytes(levels)) if levels else None
         ws = buf.bytes("accel_ws", max(lib.nb_accel_workspace_bytes(n, dim),
                                        lib.nb_max_dist_workspace_bytes(n) if levels else 0))
+        # Energy tracking (main.py:164-175, crash_point_test.py:190-197): when the potential energy was read since the
+        # previous span, the LAST force pass of this span also accumulates the per-target potentials (one more packed
+        # op per pair) and leaves PE of the final positions on the device — no second O(N²) pass at the next read.
+        pe_dev = None
+        if getattr(self, "_pe_wanted", False) and _FUSE_PE and self._pe_fusable(mode, code):
+            pe_dev = torch.empty(1, dtype=torch.float64, device=x.device)
+        self._pe_wanted = False
         with L.on_device(x.device):
             L.check(lib.nb_run_ticks(L.ptr(x_in), L.ptr(v_in), L.ptr(a_in), L.ptr(x), L.ptr(v), L.ptr(a), L.ptr(m), n, dim,
                                      code, L.dtype_code(m),
                                      L.MODE_CODES[mode.value], levels, snap_levels, float(self.G), float(self.softening_sq),
                                      float(min_dist_sq), float(self.dt), int(ticks), int(uni), m0, L.ptr(packed), L.ptr(table),
                                      L.ptr(buf.scalars), L.ptr(ws), ws.numel(), int(n <= self.GRAPH_MAX_STARS),
-                                     L.stream_ptr(x.device)), "nb_run_ticks")
+                                     L.ptr(pe_dev), L.stream_ptr(x.device)), "nb_run_ticks")
         self._packed_key = self._packed_cache_key(x, m, packed)      # packed holds the records of the final positions
         self.positions, self.velocities, self.accelerations = x, v, a
         self.tick += int(ticks)
+        if pe_dev is not None:
+            self._pe_cache = (self._pe_key(x, m), _DeferredPE(pe_dev, float(self.G), torch.promote_types(x.dtype, m.dtype)), x, m)
+
+    @staticmethod
+    def _pe_fusable(mode, code) -> bool:
+        """The force pass sees the reference's potential-energy d² (unquantised, state dtype) only in these cases."""
+        return (mode == PrecisionMode.FLOAT32 and code == L.NB_F32) or (mode == PrecisionMode.FLOAT64 and code == L.NB_F64)
+
+    def _pe_key(self, x, m):
+        return (x.data_ptr(), x._version, m.data_ptr(), m._version, tuple(x.shape), x.dtype, float(self.softening_sq),
+                float(self.G))
 
     def run(self, num_ticks: int, callback: Callable = None, callback_interval: int = 100):
         """Run `num_ticks` ticks; `callback(sim, sim.tick)` every `callback_interval` (simulation.py:145-158)."""
-        spec = self._force_spec() if self._is_stock(self, "step") else None
-        if spec is None:
-            for t in range(num_ticks):
-                self.step()
-                if callback and (t + 1) % callback_interval == 0:
-                    callback(self, self.tick)
-            return
         done = 0
         while done < num_ticks:
-            if callback:
-                until_cb = callback_interval - (done % callback_interval)
-                span = min(until_cb, num_ticks - done)
+            # re-read every span: a callback may switch precision_mode, a recognised override's level count, the
+            # state dtype, or patch step()/_compute_accelerations on the instance (the reference re-reads per tick)
+            spec = self._force_spec() if self._is_stock(self, "step") else None
+            if spec is None:
+                self.step()
+                done += 1
             else:
                 span = num_ticks - done
-            self._run_fused(span, spec)
-            done += span
+                if callback:
+                    span = min(callback_interval - (done % callback_interval), span)
+                self._run_fused(span, spec)
+                done += span
             if callback and done % callback_interval == 0:
                 callback(self, self.tick)
 
@@ -371,11 +418,15 @@ class GalaxySimulation:
         x, _, m = self._state()
         # the reference evaluates this O(N²) sum two or three times per metrics collection on an unchanged state
         # (metrics.py:174-175 -> simulation.py:196, main.py:166-167): remember the last value per (tensor, version)
-        key = (x.data_ptr(), x._version, m.data_ptr(), m._version, tuple(x.shape), x.dtype, float(self.softening_sq),
-               float(self.G))
-        cached = getattr(self, "_pe_cache", None)
+        key = self._pe_key(x, m)
+        self._pe_wanted = True                    # the next fused span ends with a potential-carrying force pass
+        cached = None if _NO_CACHE else getattr(self, "_pe_cache", None)
         if cached is not None and cached[0] == key and cached[2] is x and cached[3] is m:
-            return cached[1]
+            value = cached[1]
+            if isinstance(value, _DeferredPE):    # left on the device by the last force pass: read it once
+                value = value.read(self._as_python_float)
+                self._pe_cache = (key, value, x, m)
+            return value
         out, dtype = self._potential_sum_device(x, m)
         # the kernel sums unordered pairs i < j
         value = self._as_python_float(-float(self.G) * out.item(), dtype)
@@ -401,7 +452,14 @@ class GalaxySimulation:
         """A zero-argument callable that returns get_total_energy() of the CURRENT state; the kernels are enqueued now,
         the two scalars are read when it is called (after a synchronisation of the caller's choosing)."""
         ke, kdt = self._kinetic_sum_device()
-        pe, pdt = self._potential_sum_device()
+        x, _, m = self._state()
+        self._pe_wanted = True
+        cached = None if _NO_CACHE else getattr(self, "_pe_cache", None)
+        if cached is not None and cached[0] == self._pe_key(x, m) and cached[2] is x and cached[3] is m \
+                and isinstance(cached[1], _DeferredPE):
+            pe, pdt = cached[1].dev, cached[1].dtype          # left behind by the span's last force pass
+        else:
+            pe, pdt = self._potential_sum_device(x, m)
         ke_host = torch.empty(1, dtype=torch.float64, pin_memory=True)
         pe_host = torch.empty(1, dtype=torch.float64, pin_memory=True)
         ke_host.copy_(ke, non_blocking=True)
@@ -450,5 +508,7 @@ def run_comparison(
         sim.run(num_ticks, callback=record, callback_interval=callback_interval)
         torch.cuda.synchronize(sim.positions.device)
         history["energies"] = [e() for e in history["energies"]]
+        # hand back pageable tensors: long histories at large N must not keep page-locked memory alive
+        history["positions"] = [h.clone() if h.is_pinned() else h for h in history["positions"]]
         results[mode.value] = {"final_state": sim.get_state(), "history": history, "simulation": sim}
     return results

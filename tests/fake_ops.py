@@ -153,6 +153,10 @@ class FakeOps:
             scalars[L.SLOT_ACC_MAX] = max(int(scalars[L.SLOT_ACC_MAX]), key(acc.max().item()))
         return acc
 
+    def accel_potential(self, packed, n_src, x_tgt, m_tgt, mode, G, eps_sq, uniform=(False, 0.0)):
+        acc = self.accel(packed, n_src, x_tgt, mode, G, eps_sq, None, 0, None)
+        return acc, self.potential(packed, n_src, x_tgt, m_tgt, eps_sq)
+
     def potential(self, packed, n_src, x_tgt, m_tgt, eps_sq, tgt_offset=0):
         _, d2, m = self._pairs(packed, n_src, x_tgt, eps_sq)
         inv = 1.0 / torch.sqrt(d2.double())

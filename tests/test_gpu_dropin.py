@@ -27,3 +27,23 @@ def test_reference_style_driver_runs_unchanged(tmp_path):
         assert drift < (0.05 if mode == "int4_sim" else 1e-3), (mode, drift)
     # a user-overridden _compute_accelerations (PyTorch on CUDA tensors) goes through the same integrator kernels
     assert s["override_vs_custom_rel"] < 1e-5
+
+
+def test_c2_sized_sweep_runs_unchanged(tmp_path):
+    """BASELINE configs[1]: `main.py --stars 10000` with the five-mode precision sweep, at its stated size, through the
+    stand-in driver (the reference's own main.py cannot travel to the GPU box; same call sequence, main.py:99-208)."""
+    out = tmp_path / "summary.json"
+    cmd = [sys.executable, "-m", "nbody_cosmological_simulation_b200.run_script",
+           os.path.join(ROOT, "tests", "scripts", "reference_style_driver.py"), "--stars", "10000", "--ticks", "200",
+           "--compare", "float64,float32,float16,int8,int4", "--output", str(tmp_path / "plots"), "--json", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    s = json.load(open(out))
+    e64 = s["float64"]["energy"]
+    for mode in ("float64", "float32", "float16", "int8_sim", "int4_sim"):
+        assert s[mode]["ticks"] == [0, 100, 200] and s[mode]["tick"] == 200
+        e = s[mode]["energy"]
+        assert abs(e[0] - e64[0]) <= 3e-6 * abs(e64[0])                  # same initial state in every mode
+        drift = abs(e[-1] - e[0]) / abs(e[0])
+        assert drift < (0.05 if mode == "int4_sim" else 2e-3 if mode == "int8_sim" else 1e-4), (mode, drift)
+    assert s["override_vs_custom_rel"] < 1e-5

@@ -122,3 +122,54 @@ def test_run_comparison_history_equals_the_reference_style_recorder():
             assert a.device.type == "cpu" and a.dtype == b.dtype and torch.equal(a, b)
         assert res[mode.value]["final_state"]["tick"] == 60 and res[mode.value]["simulation"].tick == 60
         assert torch.equal(res[mode.value]["final_state"]["positions"], sim.positions)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the hook choice is re-read like the reference re-reads it: every tick, on the instance as well as on the class
+# ---------------------------------------------------------------------------------------------------
+def test_callback_that_switches_precision_mode_takes_effect_immediately():
+    import types
+    import nbody_cosmological_simulation_b200 as nb
+    torch.manual_seed(5)
+    pos, vel, mass = nb.create_disk_galaxy(900, device=torch.device("cuda:0"))
+
+    def switch(sim, tick):
+        if tick == 20:
+            sim.precision_mode = nb.PrecisionMode.INT4_SIM
+
+    a = nb.GalaxySimulation(pos, vel, mass, precision_mode=nb.PrecisionMode.FLOAT32)
+    a.run(40, callback=switch, callback_interval=10)
+    b = nb.GalaxySimulation(pos, vel, mass, precision_mode=nb.PrecisionMode.FLOAT32)
+    for t in range(40):                                # the reference's loop: the mode is read inside every step
+        b.step()
+        switch(b, b.tick)
+    assert torch.equal(a.positions, b.positions) and torch.equal(a.velocities, b.velocities)
+    c = nb.GalaxySimulation(pos, vel, mass, precision_mode=nb.PrecisionMode.FLOAT32)
+    c.run(40)
+    assert not torch.equal(a.positions, c.positions)   # the switch really changed the trajectory
+
+
+def test_instance_level_patch_of_the_force_hook_is_honoured():
+    import types
+    import nbody_cosmological_simulation_b200 as nb
+    torch.manual_seed(6)
+    pos, vel, mass = nb.create_disk_galaxy(300, device=torch.device("cuda:0"))
+    sim = nb.GalaxySimulation(pos, vel, mass, precision_mode=nb.PrecisionMode.FLOAT32)
+    calls = []
+
+    def zero_force(self):
+        calls.append(self.tick)
+        return torch.zeros_like(self.positions)
+
+    sim._compute_accelerations = types.MethodType(zero_force, sim)
+    v0 = sim.velocities.clone()
+    sim.accelerations = torch.zeros_like(sim.positions)
+    sim.run(5)
+    assert calls == [0, 1, 2, 3, 4]                    # the patched hook ran every tick, not the native force
+    assert torch.equal(sim.velocities, v0)
+    stepped = []
+    sim2 = nb.GalaxySimulation(pos, vel, mass, precision_mode=nb.PrecisionMode.FLOAT32)
+    orig = sim2.step
+    sim2.step = lambda: (stepped.append(1), orig())[1]
+    sim2.run(3)
+    assert len(stepped) == 3 and sim2.tick == 3

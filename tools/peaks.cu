@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(1024, 1) k_fp32(float* out, float seed, unsign
     float a[ILP], b = seed, c = seed * 0.5f;
     #pragma unroll
     for (int i = 0; i < ILP; ++i) a[i] = seed + i + threadIdx.x;
+    const unsigned long long g0 = gtimer();
     long long t0 = clock64();
     for (int it = 0; it < ITERS / UNROLL; ++it) {
         #pragma unroll
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(1024, 1) k_fp32(float* out, float seed, unsign
     #pragma unroll
     for (int i = 0; i < ILP; ++i) s += a[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = (unsigned long long)(t1 - t0);
+    if (threadIdx.x == 0 && blockIdx.x == 0) { cyc[0] = (unsigned long long)(t1 - t0); cyc[1] = gtimer() - g0; }
 }
 
 template <int OP>
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(1024, 1) k_fp32x2(float* out, float seed, unsi
     float2 a[ILP], b = make_float2(seed, seed * 1.0001f), c = make_float2(seed * 0.5f, seed * 0.25f);
     #pragma unroll
     for (int i = 0; i < ILP; ++i) a[i] = make_float2(seed + i + threadIdx.x, seed - i);
+    const unsigned long long g0 = gtimer();
     long long t0 = clock64();
     for (int it = 0; it < ITERS / UNROLL; ++it) {
         #pragma unroll
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(1024, 1) k_fp32x2(float* out, float seed, unsi
     #pragma unroll
     for (int i = 0; i < ILP; ++i) s += a[i].x + a[i].y;
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = (unsigned long long)(t1 - t0);
+    if (threadIdx.x == 0 && blockIdx.x == 0) { cyc[0] = (unsigned long long)(t1 - t0); cyc[1] = gtimer() - g0; }
 }
 
 template <int OP>
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(1024, 1) k_fp64(double* out, double seed, unsi
     double a[ILP], b = seed, c = seed * 0.5;
     #pragma unroll
     for (int i = 0; i < ILP; ++i) a[i] = seed + i + threadIdx.x;
+    const unsigned long long g0 = gtimer();
     long long t0 = clock64();
     for (int it = 0; it < ITERS / UNROLL; ++it) {
         #pragma unroll
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(1024, 1) k_fp64(double* out, double seed, unsi
     #pragma unroll
     for (int i = 0; i < ILP; ++i) s += a[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = (unsigned long long)(t1 - t0);
+    if (threadIdx.x == 0 && blockIdx.x == 0) { cyc[0] = (unsigned long long)(t1 - t0); cyc[1] = gtimer() - g0; }
 }
 
 // LDS.128 broadcast (all lanes read the same 16 B) — the source-tile access pattern of the force kernel
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(1024, 1) k_lds(float* out, unsigned long long*
     tile[threadIdx.x] = make_float4(threadIdx.x, 1.f, 2.f, 3.f);
     __syncthreads();
     float4 acc[4] = {};
+    const unsigned long long g0 = gtimer();
     long long t0 = clock64();
     for (int it = 0; it < ITERS / UNROLL; ++it) {
         #pragma unroll
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(1024, 1) k_lds(float* out, unsigned long long*
     }
     long long t1 = clock64();
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc[0].x + acc[1].y + acc[2].z + acc[3].w;
-    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = (unsigned long long)(t1 - t0);
+    if (threadIdx.x == 0 && blockIdx.x == 0) { cyc[0] = (unsigned long long)(t1 - t0); cyc[1] = gtimer() - g0; }
 }
 
 struct Row { std::string name; double ops_per_thread; double flop_per_op; };
@@ -135,27 +139,31 @@ int main() {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     int sms = prop.multiProcessorCount;
     int clock_khz = 0; CK(cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, 0));
-    const int threads = 1024, blocks = sms * 2;     // 2 CTAs of 1024 threads = 64 warps/SM
+    // ONE wave: every kernel here is __launch_bounds__(1024, 1) and may use up to 64 registers, so exactly one CTA of
+    // 1024 threads (32 warps, 8 per SM sub-partition x ILP 8 chains) is resident per SM.  (Round 1 launched 2 x SMs
+    // CTAs and assumed both were co-resident: its per-SM and implied-clock columns were off by 2x.)
+    const int threads = 1024, blocks = sms;
     void* out; CK(cudaMalloc(&out, (size_t)blocks * threads * 8));
-    unsigned long long* dcyc; CK(cudaMalloc(&dcyc, 8));
+    unsigned long long* dcyc; CK(cudaMalloc(&dcyc, 16));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"max_clock_mhz\": %.0f, \"results\": {\n", prop.name, sms, clock_khz / 1000.0);
     bool first = true;
     auto run = [&](const char* name, auto launch, double ops_per_thread, double flop_per_op) {
         for (int w = 0; w < 3; ++w) launch();
         CK(cudaDeviceSynchronize());
-        float best = 1e30f; unsigned long long cyc = 0;
+        float best = 1e30f; unsigned long long cyc[2] = {0, 0};
         for (int r = 0; r < 5; ++r) {
             CK(cudaEventRecord(e0)); launch(); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
-            if (ms < best) { best = ms; CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost)); }
+            if (ms < best) { best = ms; CK(cudaMemcpy(cyc, dcyc, 16, cudaMemcpyDeviceToHost)); }
         }
         CK(cudaGetLastError());
         double total_ops = ops_per_thread * threads * (double)blocks;
         double ops_per_s = total_ops / (best * 1e-3);
-        // block 0's own cycle count covers one CTA sharing its SM with another: per-SM rate from cycles
-        double lane_ops_per_clk_sm = ops_per_thread * threads * 2 / (double)cyc;
-        double eff_mhz = total_ops / (lane_ops_per_clk_sm * sms) / (best * 1e-3) / 1e6;
+        // block 0 times its own loop with clock64 (SM cycles) and globaltimer (ns): per-SM rate from its cycles (one CTA
+        // per SM), SM clock under this load = cycles / ns
+        double lane_ops_per_clk_sm = ops_per_thread * threads / (double)cyc[0];
+        double eff_mhz = cyc[1] ? (double)cyc[0] / (double)cyc[1] * 1e3 : 0.0;
         printf("%s  \"%s\": {\"ms\": %.4f, \"lane_ops_per_clk_per_sm\": %.2f, \"Tops_per_s\": %.3f, \"Tflops\": %.3f, \"implied_sm_mhz\": %.0f}",
                first ? "" : ",\n", name, best, lane_ops_per_clk_sm, ops_per_s / 1e12, ops_per_s * flop_per_op / 1e12, eff_mhz);
         first = false;
