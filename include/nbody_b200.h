@@ -243,6 +243,72 @@ int nb_radius_kth(const void* pos, int64_t n, int dim, int dtype, int64_t k, voi
 int nb_speed_moments(const void* vel, int64_t n, int dim, int dtype, double* out, void* workspace,
                      int64_t workspace_bytes, void* stream);
 
+/* compute_bound_fraction (metrics.py:98-145) without a sort and without gathering state.  The reference ranks the
+ * stars by distance from the centre of mass, takes the cumulative mass in that order and calls a star bound when
+ * |v| < sqrt(2 G M_enclosed / max(r, 0.1)).  Only the verdict is needed and it is monotone in M_enclosed, so a mass
+ * histogram over nb_radius_bins() monotone radius bins brackets every star's enclosed mass; stars whose verdict is the
+ * same at both ends of the bracket are counted at once, the few others ("doubt") get their exact enclosed mass from a
+ * brute-force sweep.  Every stage is additive over i-range shards (all-reduce the arrays between the stages):
+ *   1. nb_mass_moments           out[0..dim-1] = Σ m_i x_ik, out[dim] = Σ m_i                   metrics.py:118-119
+ *   2. nb_radius_mass_histogram  hist[bin(r_i)] += m_i, r about `centre` (dim values, state dtype) metrics.py:122
+ *   3. nb_exclusive_scan_f64     prefix[b] = Σ_{b' < b} hist[b']
+ *   4. nb_bound_classify         counters[0] += stars bound for certain; counters[1] += stars in doubt, whose records
+ *                                (nb_doubt_record_bytes() each) are appended to doubt_records (up to doubt_capacity;
+ *                                size it for n to be safe); index_base = global index of local star 0 (tie order)
+ *   5. nb_bound_resolve          partial[d] += Σ_{local j} m_j [r_j < r_d or (r_j == r_d and index_j <= index_d)]
+ *   6. nb_bound_finish           counters[0] += doubt stars bound given their exact enclosed mass   metrics.py:133-139
+ * counters: uint64[2], zeroed by the caller; hist / partial: doubles zeroed by the caller. */
+int64_t nb_radius_bins(void);
+int64_t nb_doubt_record_bytes(void);
+int nb_mass_moments(const void* pos, const void* mass, int64_t n, int dim, int dtype, int mass_dtype, double* out,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+int nb_radius_mass_histogram(const void* pos, const void* mass, const void* centre, int64_t n, int dim, int dtype,
+                             int mass_dtype, double* hist, void* stream);
+int nb_exclusive_scan_f64(const double* in, double* out, int64_t count, void* stream);
+int nb_bound_classify(const void* pos, const void* vel, const void* mass, const void* centre, int64_t n,
+                      int64_t index_base, int dim, int dtype, int mass_dtype, double G, const double* hist,
+                      const double* prefix, uint64_t* counters, void* doubt_records, int64_t doubt_capacity,
+                      void* stream);
+int nb_bound_resolve(const void* pos, const void* mass, const void* centre, int64_t n, int64_t index_base, int dim,
+                     int dtype, int mass_dtype, const void* doubt_records, int64_t n_doubt, double* partial,
+                     void* stream);
+int nb_bound_finish(const void* doubt_records, int64_t n_doubt, const double* enclosed, int dtype, int mass_dtype,
+                    double G, uint64_t* counters, void* stream);
+/* One 8-bit digit pass of nb_radius_kth's radix select, exposed for sharded runs: counts[d] += local radii whose key
+ * matches `prefix` above bit shift+8 and has digit d at `shift` (a multiple of 8); all-reduce counts, pick the digit
+ * that holds rank k, repeat towards shift 0.  counts: uint64[256], zeroed by the caller. */
+int nb_radius_digit_histogram(const void* pos, int64_t n, int dim, int dtype, int shift, uint64_t prefix,
+                              uint64_t* counts, void* stream);
+
+/* ---- initial conditions at scale: galaxy.py:10-92, 142-211 as counter-based generators ----
+ * Star i's random draws are Philox4x32-10(key = seed, counter = (i, stream)), so any partition of [0, num_stars) into
+ * ranges [start, start+count) yields the same galaxy bit for bit: an i-range shard generates only its own slice.  Same
+ * distributions and fp32 formulas as the reference; NOT torch's random stream (galaxy.create_disk_galaxy keeps that).
+ * Global quantities are partition independent: the mean circular speed is accumulated as Σ round(v · nb_init_vsum_scale())
+ * in int64 (exact under all-reduce), ranks in radius order come from a counting sort every rank can rebuild itself.
+ *   nb_disk_galaxy_phase1      pos (count,2), noise-free tangential vel (count,2), mass (count,) — any may be NULL —
+ *                              and vsum_fixed[0] += Σ round(v_circ · scale)                          galaxy.py:33-88
+ *   nb_galaxy_add_dispersion   vel += N(0,1) · dispersion (Box-Muller on the star's Philox words; stream_id 0 for the
+ *                              disk recipe, 1 for the halo recipe's second draw)                     galaxy.py:90,207
+ *   nb_disk_radius_histogram   hist[bin(r_i)] += 1 over ALL stars (radii regenerated, nothing stored); nb_radius_bins() doubles
+ *   nb_disk_radius_scatter     counting sort of all radii by bin: sorted_r / sorted_idx (num_stars each), cursor: uint32
+ *                              per bin, zeroed; prefix = exclusive scan of hist
+ *   nb_halo_phase1             local stars: exact rank inside their bin (ties by index) = enclosed visible mass,
+ *                              + analytic NFW, circular speed, tangential vel, vsum_fixed            galaxy.py:176-204 */
+double nb_init_vsum_scale(void);
+int nb_disk_galaxy_phase1(int64_t num_stars, double galaxy_radius, double core_mass_fraction, uint64_t seed,
+                          int64_t start, int64_t count, float* pos, float* vel, float* mass, int64_t* vsum_fixed,
+                          void* stream);
+int nb_galaxy_add_dispersion(uint64_t seed, int stream_id, int64_t start, int64_t count, double dispersion, float* vel,
+                             void* stream);
+int nb_disk_radius_histogram(int64_t num_stars, double galaxy_radius, double core_mass_fraction, uint64_t seed,
+                             double* hist, void* stream);
+int nb_disk_radius_scatter(int64_t num_stars, double galaxy_radius, double core_mass_fraction, uint64_t seed,
+                           const double* prefix, uint32_t* cursor, float* sorted_r, uint32_t* sorted_idx, void* stream);
+int nb_halo_phase1(int64_t num_stars, double halo_radius, double dm_mass_ratio, int64_t start, int64_t count,
+                   const float* pos, const double* hist, const double* prefix, const float* sorted_r,
+                   const uint32_t* sorted_idx, float* vel, int64_t* vsum_fixed, void* stream);
+
 /* ---- free-standing quantisers: quantization.py:74-127 -------------------------------------- */
 int nb_reset_scalars(int64_t* scalars, void* stream);
 /* scalars[VAL_MIN/VAL_MAX] = min/max of `in` (after clamp(min=clamp_min) and log() when log_space). */

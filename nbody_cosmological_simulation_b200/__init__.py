@@ -10,10 +10,12 @@ from . import _lib
 from .quantization import PrecisionMode, get_mode_from_string, describe_mode
 from .simulation import GalaxySimulation, run_comparison
 from .metrics import SimulationMetrics, collect_metrics, compute_rotation_curve
-from .galaxy import create_disk_galaxy, create_test_galaxy, create_galaxy_with_halo, nfw_enclosed_mass
+from .galaxy import (create_disk_galaxy, create_test_galaxy, create_galaxy_with_halo, nfw_enclosed_mass,
+                     create_disk_galaxy_sharded, create_galaxy_with_halo_sharded)
 
 __all__ = [
     "PrecisionMode", "get_mode_from_string", "describe_mode", "GalaxySimulation", "run_comparison",
     "SimulationMetrics", "collect_metrics", "compute_rotation_curve", "create_disk_galaxy",
-    "create_test_galaxy", "create_galaxy_with_halo", "nfw_enclosed_mass",
+    "create_test_galaxy", "create_galaxy_with_halo", "nfw_enclosed_mass", "create_disk_galaxy_sharded",
+    "create_galaxy_with_halo_sharded",
 ]

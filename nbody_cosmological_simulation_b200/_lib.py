@@ -63,6 +63,21 @@ PROTOTYPES = {
     "nb_metrics_workspace_bytes": (c_int64, []),
     "nb_radius_kth": (c_int, [_P, c_int64, c_int, c_int, c_int64, _P, _P, c_int64, _P]),
     "nb_speed_moments": (c_int, [_P, c_int64, c_int, c_int, _P, _P, c_int64, _P]),
+    "nb_radius_bins": (c_int64, []),
+    "nb_doubt_record_bytes": (c_int64, []),
+    "nb_mass_moments": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, _P, c_int64, _P]),
+    "nb_radius_mass_histogram": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
+    "nb_exclusive_scan_f64": (c_int, [_P, _P, c_int64, _P]),
+    "nb_bound_classify": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_double, _P, _P, _P, _P, c_int64, _P]),
+    "nb_bound_resolve": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P, c_int64, _P, _P]),
+    "nb_bound_finish": (c_int, [_P, c_int64, _P, c_int, c_int, c_double, _P, _P]),
+    "nb_radius_digit_histogram": (c_int, [_P, c_int64, c_int, c_int, c_int, ctypes.c_uint64, _P, _P]),
+    "nb_init_vsum_scale": (c_double, []),
+    "nb_disk_galaxy_phase1": (c_int, [c_int64, c_double, c_double, ctypes.c_uint64, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "nb_galaxy_add_dispersion": (c_int, [ctypes.c_uint64, c_int, c_int64, c_int64, c_double, _P, _P]),
+    "nb_disk_radius_histogram": (c_int, [c_int64, c_double, c_double, ctypes.c_uint64, _P, _P]),
+    "nb_disk_radius_scatter": (c_int, [c_int64, c_double, c_double, ctypes.c_uint64, _P, _P, _P, _P, _P]),
+    "nb_halo_phase1": (c_int, [c_int64, c_double, c_double, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nb_reset_scalars": (c_int, [_P, _P]),
     "nb_tensor_minmax": (c_int, [_P, c_int64, c_int, c_int, c_double, _P, _P]),
     "nb_grid_quantize": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P]),

@@ -6,7 +6,7 @@ OUT="${HERE}/../libnbody_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden
        --expt-relaxed-constexpr -fmad=false -Xptxas -v)   # -fmad=false: every FMA in this library is written explicitly; nvcc otherwise contracts even __fmul2_rn+__fadd2_rn
-SRCS=(api.cu integrate.cu accel.cu quantize.cu maxdist.cu energy.cu metrics.cu runtime.cu)
+SRCS=(api.cu integrate.cu accel.cu quantize.cu maxdist.cu energy.cu metrics.cu runtime.cu galaxy_init.cu)
 OBJS=()
 mkdir -p "${HERE}/build"
 pids=()

@@ -253,20 +253,21 @@ class ShardedGalaxySimulation:
         return self.get_kinetic_energy() + self.get_potential_energy()
 
     def collect_metrics(self, tick: int, metrics) -> None:
-        """`metrics.collect_metrics` (reference metrics.py:159-179) for a sharded run: the O(N²) energies use the
-        sharded reductions; the O(N log N) remainder (radius percentile, bound fraction, dispersion, rotation curve)
-        runs on the gathered state, identically on every rank, so every rank appends the same values."""
+        """`metrics.collect_metrics` (reference metrics.py:159-179) for a sharded run WITHOUT gathering the state: the
+        O(N²) energies use the sharded reductions, the O(N) remainder runs the same native stages on the local slice and
+        exchanges histograms / scalars only (metrics.LocalComm protocol).  Every rank appends the same values."""
         from . import metrics as M
-        pos, vel, mass = self.gather(self.positions), self.gather(self.velocities), self.gather(self.masses)
+        comm = ShardComm(self)
+        pos, vel, mass = self.positions, self.velocities, self.masses
         metrics.ticks.append(tick)
         ke, pe = self.get_kinetic_energy(), self.get_potential_energy()
         metrics.kinetic_energy.append(ke)
         metrics.potential_energy.append(pe)
         metrics.total_energy.append(ke + pe)
-        metrics.galaxy_radius_90.append(M.compute_galaxy_radius(pos, 90))
-        metrics.bound_fraction.append(M.compute_bound_fraction(pos, vel, mass, self.G))
-        metrics.velocity_dispersion.append(M.compute_velocity_dispersion(vel))
-        metrics.rotation_curves.append(M.compute_rotation_curve(pos, vel))
+        metrics.galaxy_radius_90.append(M.galaxy_radius_sharded(pos, 90, comm))
+        metrics.bound_fraction.append(M.bound_fraction_sharded(pos, vel, mass, self.G, comm))
+        metrics.velocity_dispersion.append(M.velocity_dispersion_sharded(vel, comm))
+        metrics.rotation_curves.append(M.rotation_curve_sharded(pos, vel, 20, None, comm))
 
     def gather(self, local: torch.Tensor) -> torch.Tensor:
         """Full (N, …) tensor from the local slices (variable slice sizes -> padded all_gather)."""
@@ -283,3 +284,45 @@ class ShardedGalaxySimulation:
     def get_state(self) -> dict:
         return {"positions": self.gather(self.positions), "velocities": self.gather(self.velocities),
                 "masses": self.gather(self.masses), "tick": self.tick, "precision_mode": self.precision_mode.value}
+
+
+class ShardComm:
+    """metrics.LocalComm over torch.distributed for the i-range shards of a ShardedGalaxySimulation."""
+
+    def __init__(self, sim: ShardedGalaxySimulation):
+        self.sim = sim
+        self.world = sim.world
+        self.index_base = sim.plan.start[sim.rank]
+
+    def n_total(self, n_local: int) -> int:
+        return self.sim.num_stars
+
+    def sum_(self, t):
+        self.sim._all_reduce(t, dist.ReduceOp.SUM)
+        return t
+
+    def max_(self, t):
+        self.sim._all_reduce(t, dist.ReduceOp.MAX)
+        return t
+
+    def gather_rows(self, t):
+        if self.world == 1:
+            return t
+        counts = torch.zeros(self.world, dtype=torch.int64, device=t.device)
+        counts[self.sim.rank] = t.shape[0]
+        self.sum_(counts)
+        counts = counts.tolist()
+        rows = max(max(counts), 1)
+        pad = torch.zeros((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[: t.shape[0]] = t
+        out = torch.empty((self.world * rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, pad, group=self.sim.group)
+        return torch.cat([out[r * rows: r * rows + counts[r]] for r in range(self.world)], dim=0)
+
+    def gather_scalars(self, values):
+        if self.world == 1:
+            return [list(values)]
+        v = torch.zeros(self.world, len(values), dtype=torch.float64, device=self.sim.device)
+        v[self.sim.rank] = torch.tensor(list(values), dtype=torch.float64)
+        self.sum_(v)
+        return v.tolist()

@@ -391,6 +391,12 @@ class GalaxySimulation:
             "precision_mode": self.precision_mode.value,
         }
 
+    def state_hash(self) -> str:
+        """sha256(positions bytes + velocities bytes)[:16] — the reference's reproducibility.hash_tensor_state (:227-232),
+        the on-disk identity of a state for parity artefacts."""
+        import hashlib
+        return hashlib.sha256(self.positions.cpu().numpy().tobytes() + self.velocities.cpu().numpy().tobytes()).hexdigest()[:16]
+
     @staticmethod
     def _as_python_float(value: float, dtype: torch.dtype) -> float:
         # the reference returns `.item()` of a tensor of this dtype
@@ -485,30 +491,72 @@ def run_comparison(
 
     The reference's recorder copies the full position array to the host and pulls two energy scalars with `.item()`
     at every callback, i.e. it drains the GPU each time.  Here the recorder only ENQUEUES: the positions go to pinned
-    host memory with an asynchronous copy, the energy kernels leave their scalars in pinned memory too, and
-    everything is read once after the run.  What the caller gets back is identical: CPU
-    tensors, Python floats, the same ticks.  A user `callback` still sees the live simulation at every interval."""
+    host memory with an asynchronous copy, the energy kernels leave their scalars in pinned memory too (the potential
+    rides on the span's last force pass where the mode allows), and everything is read once after the run
+    (SURVEY.md §8f row 4).  What the caller gets back is identical: CPU tensors, Python floats, the same ticks.  A user
+    `callback` still sees the live simulation at every interval.
+
+    State artefacts at scale — one extra keyword, taken out of `sim_kwargs` before they reach the constructor:
+      record="full"        (default) the reference's history: every star's position at every callback
+      record="decimate:K"  positions of every K-th star only (a device-side strided gather, 1/K of the traffic)
+      record="sha256"      no positions; history["state_sha256"] holds `state_hash()` of every snapshot — the format of
+                           the reference's reproducibility.hash_tensor_state (:227-232): sha256(pos bytes + vel bytes)[:16].
+                           Snapshots are hashed one callback late from two rotating pinned buffers, so the run never
+                           holds more than two of them."""
+    record = sim_kwargs.pop("record", "full")
+    stride = 1
+    if isinstance(record, str) and record.startswith("decimate:"):
+        stride = max(1, int(record.split(":", 1)[1]))
+    elif record not in ("full", "sha256"):
+        raise ValueError(f"record must be 'full', 'decimate:K' or 'sha256', got {record!r}")
     results = {}
     for mode in modes:
         print(f"\nRunning simulation with {mode.value} precision...")
         sim = GalaxySimulation(positions.clone(), velocities.clone(), masses.clone(), precision_mode=mode,
                                **sim_kwargs)
-        history = {"positions": [positions.clone().cpu()], "energies": [sim._total_energy_deferred()], "ticks": [0]}
+        history = {"positions": [], "energies": [sim._total_energy_deferred()], "ticks": [0]}
+        pending = []                                          # sha256 mode: (pinned pos, pinned vel, event) awaiting their digest
 
-        def record(s, tick, history=history):
-            x = s.positions
+        def snapshot(s, history=history, pending=pending):
+            if record == "sha256":
+                if pending:                                   # hash the previous snapshot while this one is in flight
+                    history.setdefault("state_sha256", []).append(_digest(*pending.pop(0)))
+                x, v = s.positions, s.velocities
+                hx = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+                hv = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                hx.copy_(x, non_blocking=True)
+                hv.copy_(v, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                pending.append((hx, hv, ev))
+                return
+            x = s.positions if stride == 1 else s.positions[::stride].contiguous()
             host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
             host.copy_(x, non_blocking=True)                  # ordered after the tick's kernels on the same stream
             history["positions"].append(host)
+
+        def record_cb(s, tick, history=history):
+            snapshot(s)
             history["energies"].append(s._total_energy_deferred())
             history["ticks"].append(tick)
             if callback:
                 callback(s, tick)
 
-        sim.run(num_ticks, callback=record, callback_interval=callback_interval)
+        snapshot(sim)                                         # tick 0 (the reference stores the input positions)
+        sim.run(num_ticks, callback=record_cb, callback_interval=callback_interval)
         torch.cuda.synchronize(sim.positions.device)
         history["energies"] = [e() for e in history["energies"]]
+        while pending:
+            history.setdefault("state_sha256", []).append(_digest(*pending.pop(0)))
         # hand back pageable tensors: long histories at large N must not keep page-locked memory alive
         history["positions"] = [h.clone() if h.is_pinned() else h for h in history["positions"]]
+        if stride > 1:
+            history["position_stride"] = stride
         results[mode.value] = {"final_state": sim.get_state(), "history": history, "simulation": sim}
     return results
+
+
+def _digest(host_pos, host_vel, event) -> str:
+    event.synchronize()
+    import hashlib
+    return hashlib.sha256(host_pos.numpy().tobytes() + host_vel.numpy().tobytes()).hexdigest()[:16]

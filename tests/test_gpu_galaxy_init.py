@@ -1,0 +1,160 @@
+"""Counter-based, shardable initial conditions (csrc/galaxy_init.cu) on a B200.
+
+What is checked (the random stream is this package's own Philox-per-index stream, so the reference's fixtures cannot
+pin the draws; its FORMULAS and DISTRIBUTIONS are what must match):
+  * partition independence: any split of [0, N) gives bit-identical stars, including the velocity dispersion that
+    depends on the global mean speed and, for the halo recipe, the global rank of every star in radius order;
+  * the reference's formulas (galaxy.py:33-88, 176-204) evaluated by torch on the CPU from the generated positions
+    reproduce the noise-free velocities; the enclosed visible mass equals the rank from a stable argsort + cumsum;
+  * the distributions: radii follow the truncated-exponential inverse CDF, angles are uniform, the added dispersion
+    is N(0, sigma²) with sigma = 0.1 (0.05) x mean circular speed;
+  * statistics agree with the torch-stream recipe `create_disk_galaxy` at the same N.
+"""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def _phase1(n, seed, start=0, count=None, R=10.0, cmf=0.3):
+    from nbody_cosmological_simulation_b200 import _lib as L
+    count = n - start if count is None else count
+    lib = L.load()
+    pos = torch.empty((count, 2), device=DEV)
+    vel = torch.empty((count, 2), device=DEV)
+    mass = torch.empty(count, device=DEV)
+    vsum = torch.zeros(1, dtype=torch.int64, device=DEV)
+    L.check(lib.nb_disk_galaxy_phase1(n, R, cmf, seed, start, count, L.ptr(pos), L.ptr(vel), L.ptr(mass), L.ptr(vsum),
+                                      L.stream_ptr(DEV)))
+    return pos, vel, mass, vsum
+
+
+def _reference_v_circ(r, n, R=10.0, cmf=0.3):
+    """galaxy.py:56-79 with torch on the CPU."""
+    scale, max_r, total, core = R / 3.0, R * 2.0, n * 1.0, R * 0.2
+    enc = torch.zeros_like(r)
+    inner = r < core
+    enc[inner] = cmf * total * (r[inner] / core) ** 2
+    outer = ~inner
+    disk = (1 - cmf) * total * (1 - (1 + r[outer] / scale) * torch.exp(-r[outer] / scale)) / (1 - 2 * math.exp(-max_r / scale))
+    enc[outer] = cmf * total + disk
+    return torch.sqrt(0.001 * enc / r.clamp(min=0.1))
+
+
+@pytest.mark.parametrize("n", [1000, 100003])
+def test_disk_partition_independence(n):
+    import nbody_cosmological_simulation_b200 as nb
+    whole = nb.create_disk_galaxy_sharded(n, device=DEV, seed=7)
+    cuts = [0, n // 3 + 5, n // 3 + 6, n - 17, n]
+    parts = [nb.create_disk_galaxy_sharded(n, device=DEV, seed=7, start=a, count=b - a, collective=False)
+             for a, b in zip(cuts[:-1], cuts[1:])]
+    for k in range(3):
+        assert torch.equal(whole[k], torch.cat([p[k] for p in parts], 0))
+    other = nb.create_disk_galaxy_sharded(n, device=DEV, seed=8)
+    assert not torch.equal(whole[0], other[0])
+    assert whole[0].shape == (n, 2) and whole[1].shape == (n, 2) and whole[2].shape == (n,) and bool((whole[2] == 1).all())
+
+
+def test_disk_formulas_match_the_reference_recipe():
+    n = 50000
+    pos, vel, mass, vsum = _phase1(n, seed=3)
+    pos, vel = pos.cpu(), vel.cpu()
+    r = torch.sqrt((pos ** 2).sum(-1))
+    assert float(r.min()) >= 0.1 - 1e-6 and float(r.max()) <= 20.0 + 1e-5
+    v_ref = _reference_v_circ(r, n)
+    speed = torch.sqrt((vel ** 2).sum(-1))
+    np.testing.assert_allclose(speed.numpy(), v_ref.numpy(), rtol=5e-6)                     # radius recomputed from x, y: ~1 ulp
+    assert float(((pos * vel).sum(-1).abs() / (r * speed)).max()) <= 2e-6                   # tangential
+    assert bool(((pos[:, 0] * vel[:, 1] - pos[:, 1] * vel[:, 0]) > 0).all())                # counter-clockwise, as the reference
+    from nbody_cosmological_simulation_b200 import _lib as L
+    mean_fixed = float(vsum.item()) / L.load().nb_init_vsum_scale() / n
+    assert abs(mean_fixed - float(speed.double().mean())) <= 1e-6 * mean_fixed
+
+
+def test_disk_distributions():
+    import nbody_cosmological_simulation_b200 as nb
+    n = 400000
+    pos0, vel0, _, vsum = _phase1(n, seed=11)
+    pos, vel, mass = nb.create_disk_galaxy_sharded(n, device=DEV, seed=11)
+    assert torch.equal(pos, pos0)
+    r = torch.sqrt((pos.double() ** 2).sum(-1)).cpu().numpy()
+    scale, max_r = 10.0 / 3.0, 20.0
+    inside = r > 0.1 + 1e-6                                          # the clamp piles the innermost stars up at 0.1
+    u = (1 - np.exp(-r / scale)) / (1 - math.exp(-max_r / scale))   # inverse of the sampling map: must be uniform
+    us = np.sort(u[inside])
+    lo = (1 - math.exp(-0.1 / scale)) / (1 - math.exp(-max_r / scale))
+    ks = np.abs((us - lo) / (1 - lo) - (np.arange(us.size) + 0.5) / us.size).max()
+    assert ks <= 2.5 / math.sqrt(us.size), ks
+    ang = np.arctan2(pos[:, 1].cpu().numpy(), pos[:, 0].cpu().numpy()) % (2 * math.pi)
+    ks_a = np.abs(np.sort(ang) / (2 * math.pi) - (np.arange(n) + 0.5) / n).max()
+    assert ks_a <= 2.5 / math.sqrt(n), ks_a
+    sigma = 0.1 * float(torch.sqrt((vel0.double() ** 2).sum(-1)).mean())
+    z = ((vel - vel0).double() / sigma).cpu().numpy().ravel()
+    assert abs(z.mean()) <= 4 / math.sqrt(z.size) and abs(z.std() - 1) <= 0.01
+    assert abs(np.mean(z ** 4) - 3.0) <= 0.1                         # Gaussian kurtosis
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) <= 4 / math.sqrt(n)
+
+
+def test_disk_statistics_agree_with_the_torch_stream_recipe():
+    import nbody_cosmological_simulation_b200 as nb
+    n = 200000
+    a = nb.create_disk_galaxy_sharded(n, device=DEV, seed=5)
+    torch.manual_seed(5)
+    b = nb.create_disk_galaxy(n, device=DEV)
+    ra, rb = (torch.sqrt((x[0].double() ** 2).sum(-1)) for x in (a, b))
+    for q in (0.1, 0.5, 0.9, 0.99):
+        assert abs(float(ra.quantile(q)) - float(rb.quantile(q))) <= 0.02 * float(rb.quantile(q))
+    sa, sb = (torch.sqrt((x[1].double() ** 2).sum(-1)).mean().item() for x in (a, b))
+    assert abs(sa - sb) <= 0.005 * sb
+
+
+@pytest.mark.parametrize("n", [2000, 60000])
+def test_halo_partition_independence_and_formulas(n):
+    import nbody_cosmological_simulation_b200 as nb
+    from nbody_cosmological_simulation_b200 import _lib as L
+    whole = nb.create_galaxy_with_halo_sharded(n, device=DEV, seed=9)
+    cuts = [0, n // 4 + 3, n // 2, n]
+    parts = [nb.create_galaxy_with_halo_sharded(n, device=DEV, seed=9, start=a, count=b - a, collective=False)
+             for a, b in zip(cuts[:-1], cuts[1:])]
+    for k in range(3):
+        assert torch.equal(whole[k], torch.cat([p[k] for p in parts], 0))
+    # the positions are the disk recipe's
+    assert torch.equal(whole[0], _phase1(n, seed=9)[0])
+    # noise-free halo speeds against galaxy.py:176-204 evaluated by torch on the CPU
+    pos = whole[0].cpu()
+    r = torch.sqrt((pos ** 2).sum(-1))
+    order = torch.argsort(r, stable=True)
+    enc_vis = torch.cumsum(torch.ones(n)[order], 0)[torch.argsort(order)]
+    enc_dm = nb.nfw_enclosed_mass(r, n * 5.0, 30.0)
+    v_ref = torch.sqrt(0.001 * (enc_vis + enc_dm) / r.clamp(min=0.1))
+    sigma = 0.05 * float(v_ref.double().mean())
+    speed = torch.sqrt((whole[1].cpu() ** 2).sum(-1))
+    # with the N(0, sigma²) dispersion on top: |v| − v_ref is a few sigma at most, and unbiased
+    d = (speed - v_ref).double()
+    assert float(d.abs().max()) <= 6 * sigma and abs(float(d.mean())) <= 5 * sigma / math.sqrt(n) + 0.51 * sigma ** 2 / float(v_ref.mean())
+    # and exactly, through the phase-1 entry point (no dispersion): rebuild the counting sort and compare speeds
+    lib = L.load()
+    bins = int(lib.nb_radius_bins())
+    st = L.stream_ptr(DEV)
+    hist = torch.zeros(bins, dtype=torch.float64, device=DEV)
+    L.check(lib.nb_disk_radius_histogram(n, 10.0, 0.3, 9, L.ptr(hist), st))
+    assert int(hist.sum().item()) == n
+    prefix = torch.empty_like(hist)
+    L.check(lib.nb_exclusive_scan_f64(L.ptr(hist), L.ptr(prefix), bins, st))
+    assert torch.equal(prefix, torch.cumsum(hist, 0) - hist)
+    cursor = torch.zeros(bins, dtype=torch.int32, device=DEV)
+    sr = torch.empty(n, dtype=torch.float32, device=DEV)
+    si = torch.empty(n, dtype=torch.int32, device=DEV)
+    L.check(lib.nb_disk_radius_scatter(n, 10.0, 0.3, 9, L.ptr(prefix), L.ptr(cursor), L.ptr(sr), L.ptr(si), st))
+    assert torch.equal(torch.sort(si.long())[0], torch.arange(n, device=DEV))                 # a permutation
+    v0 = torch.empty((n, 2), device=DEV)
+    vs = torch.zeros(1, dtype=torch.int64, device=DEV)
+    L.check(lib.nb_halo_phase1(n, 30.0, 5.0, 0, n, L.ptr(whole[0]), L.ptr(hist), L.ptr(prefix), L.ptr(sr), L.ptr(si), L.ptr(v0),
+                               L.ptr(vs), st))
+    speed0 = torch.sqrt((v0.cpu() ** 2).sum(-1))
+    np.testing.assert_allclose(speed0.numpy(), v_ref.numpy(), rtol=5e-6)

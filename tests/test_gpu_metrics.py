@@ -54,3 +54,67 @@ def test_collect_metrics_matches_oracle_functions(golden):
     assert abs(m.velocity_dispersion[0] - float(g["init/dispersion"])) < 1e-6 * float(g["init/dispersion"]) + 1e-9
     np.testing.assert_array_equal(np.array(m.rotation_curves[0]["num_stars_per_bin"]), g["init/rc_cnt"])
     assert abs(m.total_energy[0] - (m.kinetic_energy[0] + m.potential_energy[0])) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# compute_bound_fraction as a native histogram + doubt sweep (no sort): against the reference's argsort/cumsum formula
+# ---------------------------------------------------------------------------------------------------
+def _evolved_disk(n, seed, ticks=0, dtype=torch.float32):
+    import nbody_cosmological_simulation_b200 as nb
+    torch.manual_seed(seed)
+    pos, vel, mass = nb.create_disk_galaxy(n, device=torch.device("cpu"))
+    pos, vel, mass = pos.to(dtype), vel.to(dtype), mass.to(dtype)
+    if ticks:
+        sim = nb.GalaxySimulation(pos.to(DEV), vel.to(DEV), mass.to(DEV), precision_mode=nb.PrecisionMode.FLOAT32, dt=0.05)
+        sim.run(ticks)
+        pos, vel = sim.positions.cpu().to(dtype), sim.velocities.cpu().to(dtype)
+    return pos, vel, mass
+
+
+@pytest.mark.parametrize("n,ticks,scale", [(256, 0, 1.0), (5000, 0, 1.0), (5000, 0, 1.6), (20000, 40, 1.3), (100003, 0, 1.5)])
+def test_bound_fraction_matches_reference_formula(n, ticks, scale):
+    from nbody_cosmological_simulation_b200 import metrics as M
+    pos, vel, mass = _evolved_disk(n, 3 + n, ticks)
+    vel = vel * scale                                        # push a good part of the stars across their escape speed
+    want = ora.bound_fraction(pos, vel, mass, 0.001)
+    got = M.compute_bound_fraction(pos.to(DEV), vel.to(DEV), mass.to(DEV), 0.001)
+    assert abs(got - want) <= 2.0 / n + 1e-7, (got, want)     # at most a star or two on the v == v_esc edge
+    assert 0.02 < want < 0.9999 or scale == 1.0
+    assert M.bound_fraction_sharded.last_doubt <= max(64, n // 100)        # the histogram decides almost every star
+
+
+def test_bound_fraction_general_masses_fp64_and_3d():
+    from nbody_cosmological_simulation_b200 import metrics as M
+    n = 30000
+    pos, vel, mass = ora.uniform_box(n, seed=5, dim=3, dtype=torch.float64)
+    mass = mass * (1.0 + (torch.arange(n) % 7).double()) * 3e3
+    vel = vel * 4.0
+    want = ora.bound_fraction(pos, vel, mass, 0.001)
+    got = M.compute_bound_fraction(pos.to(DEV), vel.to(DEV), mass.to(DEV), 0.001)
+    assert abs(got - want) <= 2.0 / n
+    assert 0.05 < want < 0.95
+
+
+def test_bound_fraction_when_the_histogram_cannot_decide():
+    """Every star on the same circle: one radius bin holds everything, every verdict hangs on the argsort order inside
+    the bin -> the exact sweep decides (ties broken by index, as a stable argsort does)."""
+    from nbody_cosmological_simulation_b200 import metrics as M
+    n = 3000
+    ang = torch.linspace(0, 2 * np.pi, n + 1)[:-1]
+    rad = 5.0 + torch.arange(n, dtype=torch.float64) * 1.0e-6          # ~2 fp32 ulp apart: distinct radii, one or two bins
+    pos = torch.stack([rad * torch.cos(ang.double()), rad * torch.sin(ang.double())], 1).float()
+    mass = torch.ones(n)
+    # speeds scattered around the escape speed AT EACH STAR'S OWN RANK: the verdict needs the rank inside the bin
+    r = torch.sqrt(((pos - (pos * mass[:, None]).sum(0) / n) ** 2).sum(-1))
+    order = torch.argsort(r, stable=True)
+    rank = torch.empty(n, dtype=torch.long)
+    rank[order] = torch.arange(n)
+    f = 0.5 + torch.rand(n, generator=torch.Generator().manual_seed(1))
+    vel = torch.stack([f * torch.sqrt(2 * 0.001 * (rank.float() + 1) / r.clamp(min=0.1)), torch.zeros(n)], 1)
+    want = ora.bound_fraction(pos, vel, mass, 0.001)
+    got = M.compute_bound_fraction(pos.to(DEV), vel.to(DEV), mass.to(DEV), 0.001)
+    assert M.bound_fraction_sharded.last_doubt >= n // 4
+    # fp32 radii recomputed from rounded coordinates tie for ~15 % of the stars; a tie order that differs from the CPU
+    # argsort moves a rank by one or two, which matters only for stars within ~1/rank of their escape speed
+    assert abs(got - want) <= 0.01, (got, want)
+    assert 0.3 < want < 0.7
