@@ -260,7 +260,8 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(ticks):
-            timer.arm()                           # events around the pair kernel of this step (inside nb_run_ticks / ops.accel)
+            # events around the pair kernel(s) of this step (inside nb_run_ticks / the two source windows of a sharded tick)
+            timer.arm(sim.pair_launches_next_tick() if hasattr(sim, "pair_launches_next_tick") else 1)
             sim.step()
             if per_tick:
                 per_tick(sim)
@@ -288,8 +289,9 @@ def main():
     value = interactions_per_step / (ms_per_step * 1e-3)
     f_ms = max_over_ranks(sum(force_ms) / len(force_ms))
     # kernels of this library per step and rank: 1 GPU: kick-drift(+packed emit), pair kernel, closing kick (which also
-    # reduces the j-split partial sums) = 3; sharded: + the partial-sum reduction as its own launch = 4 (+1 NCCL all-gather)
-    launches = K * (3 if world == 1 else 4)
+    # reduces the j-split partial sums) = 3; sharded: kick-drift, pair kernel on the own slot, pair kernel on the gathered
+    # slots, partial-sum reduction, closing kick = 5 (+1 NCCL all-gather); profiles/r02/bench_n1_launch_list.csv
+    launches = K * (3 if world == 1 else 5)
 
     # -------- end to end through the public API with host buffers (pinned), same metric --------
     sl = sim.plan.slice(rank) if world > 1 else slice(0, N_PARTICLES)
@@ -447,7 +449,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_dict(world),
-                "parallelism": f"i-range shards x{world}, packed sources all-gathered per tick" if world > 1 else "single GPU",
+                "parallelism": (f"i-range shards x{world}; packed sources all-gathered in place per tick on a side stream, hidden behind "
+                                f"the pair kernel over the rank's own slot") if world > 1 else "single GPU",
                 "l2": "flushed between steps (192 MiB write inside the timed region); the 16 MiB packed source set is "
                       "re-read from L2 by design",
                 "tflops_at_20_flop": value * FLOP_PER_INTERACTION / 1e12,

@@ -155,10 +155,26 @@ int nb_accel_potential(const void* packed_src, int64_t n_src, const void* pos_tg
                        double mass_value, void* acc_out, double* pe_out, void* workspace, int64_t workspace_bytes,
                        void* stream);
 
-/* Instrumentation: record the CUDA events `start_event` / `stop_event` (cudaEvent_t as void*) immediately before and
- * after the NEXT pair-kernel launch issued by this host thread (inside nb_accel, nb_accel_potential or nb_run_ticks),
- * on that launch's stream; one-shot.  bench.py times the dominant kernel with it without leaving the default path. */
-int nb_profile_next_force(void* start_event, void* stop_event);
+/* Windowed force evaluation for i-range-sharded ticks (float modes only).  nb_accel_window streams the source chunks
+ * [first_chunk, first_chunk + n_chunks) of the packed set — taken modulo ring_chunks when ring_chunks > 0, so a window may
+ * wrap past the last chunk — and APPENDS its j-split partial sums to `workspace` behind the `splits_before` split slots
+ * earlier windows of the same evaluation wrote; *splits_total_out = splits_before + the slots it added (max_splits > 0 caps
+ * them).  nb_accel_finish reduces all slots into acc_out exactly as nb_accel does.  A sharded tick runs the window of
+ * the rank's OWN packed slot while the all-gather of the other ranks' slots is still in flight, then the ring window over
+ * the remaining slots: the collective hides behind 1/P of the pair work. */
+int nb_accel_window(const void* packed_src, int64_t n_src, int64_t first_chunk, int64_t n_chunks, int64_t ring_chunks,
+                    const void* pos_tgt, int64_t n_tgt, int dim, int dtype, int mode, double G, double eps_sq,
+                    int uniform_mass, double mass_value, void* workspace, int64_t workspace_bytes, int splits_before,
+                    int max_splits, int* splits_total_out, void* stream);
+int nb_accel_finish(const void* workspace, int splits_total, int64_t n_tgt, int dim, int dtype, int mode, double G,
+                    int uniform_mass, double mass_value, void* acc_out, void* stream);
+
+/* Instrumentation: record the CUDA event `start_event` (cudaEvent_t as void*) immediately before the NEXT pair-kernel
+ * launch issued by this host thread (inside nb_accel, nb_accel_potential, nb_accel_window or nb_run_ticks) and
+ * `stop_event` immediately after the `launches`-th one from there (1 = the same launch; 2 = the two windows of a
+ * sharded tick, which may sit on different streams), each on its launch's stream; one-shot.  bench.py times the dominant
+ * kernel with it without leaving the default path. */
+int nb_profile_next_force(void* start_event, void* stop_event, int launches);
 /* Plain cudaEvent_t helpers for the hook above (so that a caller needs no CUDA runtime binding of its own):
  * create (timing enabled), elapsed milliseconds (synchronises on stop_event — host-blocking, instrumentation only),
  * destroy. */

@@ -51,7 +51,10 @@ PROTOTYPES = {
                              c_double, c_int64, c_int, c_double, _P, _P, _P, _P, c_int64, c_int, _P, _P]),
     "nb_accel_potential": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_double, c_double, c_int, c_double,
                                    _P, _P, _P, c_int64, _P]),
-    "nb_profile_next_force": (c_int, [_P, _P]),
+    "nb_accel_window": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, c_int, c_int, c_int, c_double, c_double, c_int,
+                                c_double, _P, c_int64, c_int, c_int, POINTER(c_int), _P]),
+    "nb_accel_finish": (c_int, [_P, c_int, c_int64, c_int, c_int, c_int, c_double, c_int, c_double, _P, _P]),
+    "nb_profile_next_force": (c_int, [_P, _P, c_int]),
     "nb_event_create": (c_int, [POINTER(c_void_p)]),
     "nb_event_elapsed_ms": (c_int, [_P, _P, POINTER(ctypes.c_float)]),
     "nb_event_destroy": (c_int, [_P]),
@@ -168,15 +171,16 @@ class ForceTimer:
         self.lib = load()
         self.pairs = []
 
-    def arm(self):
+    def arm(self, launches: int = 1):
+        """Time from the next pair-kernel launch to the end of the `launches`-th one (2: both windows of a sharded tick)."""
         e0, e1 = c_void_p(), c_void_p()
         check(self.lib.nb_event_create(ctypes.byref(e0)), "nb_event_create")
         check(self.lib.nb_event_create(ctypes.byref(e1)), "nb_event_create")
-        check(self.lib.nb_profile_next_force(e0, e1), "nb_profile_next_force")
+        check(self.lib.nb_profile_next_force(e0, e1, int(launches)), "nb_profile_next_force")
         self.pairs.append((e0, e1))
 
     def disarm(self):
-        check(self.lib.nb_profile_next_force(None, None), "nb_profile_next_force")
+        check(self.lib.nb_profile_next_force(None, None, 1), "nb_profile_next_force")
 
     def times_ms(self):
         """Durations of the armed launches (synchronises); events are released."""

@@ -37,7 +37,9 @@ enum QMode { Q_F32 = 0, Q_F16 = 1, Q_BF16 = 2, Q_LUT = 3, Q_F64 = 4, Q_LUTF = 5 
 
 struct AccelArgs {
     const char* src;          // packed sources
-    int64_t n_chunks;
+    int64_t n_chunks;         // chunks this launch streams (the whole packed set, or a window of it)
+    int64_t chunk0;           // first chunk of the window
+    int64_t ring;             // > 0: chunk indices are taken modulo this (a window that wraps past the last chunk)
     const void* pos_tgt;      // (n_tgt, DIM) state dtype
     int64_t n_tgt;
     int chunks_per_split;
@@ -49,6 +51,8 @@ struct AccelArgs {
     int lut_rep;              // shared-memory replication of the level table (1, 2, 4 or 8 copies, see accel_kernel)
     float neg_zero;           // -0.0f, passed at run time so that the compiler cannot fold fma(d, d, -0) back into a mul
     float uniform_mass;       // Q_LUTF: != 0 when every real source has this mass (the per-pair mass multiply is dropped)
+    int splits_before;        // windowed evaluation: split slots already used by earlier windows
+    int max_splits;           // > 0: cap on the split count of this launch
 };
 
 // Level table layout (Q_LUT): float4 entry[k] = { T_{k+1}, g_k, g_{k+1}, 0 } for k = 0..L-1, preceded by a
@@ -627,7 +631,7 @@ __global__ void __launch_bounds__(Consumer::THREADS + 32, LUTKIND == 2 ? NB_LUTF
     if constexpr (LUTKIND == 1) cons.levels_m1_f = (float)(a.levels - 1);
     const int64_t c0 = (int64_t)blockIdx.y * a.chunks_per_split;
     const int64_t c1 = min(a.n_chunks, c0 + (int64_t)a.chunks_per_split);
-    stream_sources(a.src, c0, c1, cons);
+    stream_sources(a.src, a.chunk0 + c0, a.chunk0 + c1, cons, a.ring);
     if (is_consumer) cons.store(a);
 }
 
@@ -699,18 +703,22 @@ constexpr int64_t kPhiBlockBytes = 16 * 1024;        // per-CTA partial sums of 
 
 // Instrumentation hook (nb_profile_next_force): CUDA events recorded around the NEXT pair-kernel launch of this host
 // thread, then forgotten.  bench.py uses it to time the dominant kernel inside nb_run_ticks without changing the path.
-struct ForceProfile { void* start; void* stop; };
-inline ForceProfile& force_profile() { static thread_local ForceProfile p{nullptr, nullptr}; return p; }
+struct ForceProfile { void* start; void* stop; int launches; };       // stop is recorded after the `launches`-th launch
+inline ForceProfile& force_profile() { static thread_local ForceProfile p{nullptr, nullptr, 0}; return p; }
 
 template <class Consumer, int LUTKIND>
 int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, int* splits_out, double** phi_out = nullptr) {
     AccelArgs a = a0;
+    // a windowed launch appends its split slots behind the ones earlier windows of the same evaluation wrote
+    const int splits_before = a.splits_before;
+    a.partial += (int64_t)splits_before * a.n_tgt * Consumer::DIM;
     // a PHI consumer keeps one more double per target and split (the potential), behind the acceleration partials
     const int64_t per_split = a.n_tgt * (Consumer::DIM + (Consumer::HAS_PHI ? 1 : 0)) * (int64_t)sizeof(double);
-    int64_t max_by_ws = (workspace_bytes - (Consumer::HAS_PHI ? kPhiBlockBytes : 0)) / per_split;
-    if (max_by_ws < 1) return NB_ERR_WORKSPACE_TOO_SMALL;
-    const int cap = max_splits_for(a.n_tgt, Consumer::DIM);
+    int64_t max_by_ws = (workspace_bytes - (Consumer::HAS_PHI ? kPhiBlockBytes : 0)) / per_split - splits_before;
+    const int cap = max_splits_for(a.n_tgt, Consumer::DIM) - splits_before;
     if (max_by_ws > cap) max_by_ws = cap;
+    if (max_by_ws < 1) return NB_ERR_WORKSPACE_TOO_SMALL;
+    if (a.max_splits > 0 && max_by_ws > a.max_splits) max_by_ws = a.max_splits;
     int smem = stream_smem_bytes(Consumer::DIM);
     if (LUTKIND == 1) {
         a.lut_rep = 8;                                        // as many copies as fit in 32 KB
@@ -729,11 +737,10 @@ int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, 
     a.chunks_per_split = p.chunks_per_split;
     if (Consumer::HAS_PHI) a.partial_phi = a.partial + (int64_t)p.splits * a.n_tgt * Consumer::DIM;
     ForceProfile& prof = force_profile();
-    if (prof.start) cudaEventRecord((cudaEvent_t)prof.start, st);
+    if (prof.start) { cudaEventRecord((cudaEvent_t)prof.start, st); prof.start = nullptr; }
     kern<<<dim3(p.blocks_i, p.splits), Consumer::THREADS + 32, smem, st>>>(a);
     NB_CUDA_LAUNCH_CHECK();
-    if (prof.stop) cudaEventRecord((cudaEvent_t)prof.stop, st);
-    prof.start = prof.stop = nullptr;                     // one-shot
+    if (prof.stop && --prof.launches <= 0) { cudaEventRecord((cudaEvent_t)prof.stop, st); prof.stop = nullptr; }   // one-shot
     *splits_out = p.splits;
     if (phi_out) *phi_out = a.partial_phi;
     return NB_OK;
@@ -753,7 +760,8 @@ extern "C" int64_t nb_accel_workspace_bytes(int64_t n_targets, int dim) {
 
 int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt, int dim, int dtype, int mode,
                     double G, double eps_sq, const void* level_table, int levels, int uniform_mass, double mass_value,
-                    int64_t* scalars, void* workspace, int64_t workspace_bytes, cudaStream_t st, PartialSums* out, bool want_phi) {
+                    int64_t* scalars, void* workspace, int64_t workspace_bytes, cudaStream_t st, PartialSums* out, bool want_phi,
+                    const SourceWindow* window) {
     if (!packed_src || !pos_tgt || !workspace || n_src <= 0 || n_tgt <= 0 || (dim != 2 && dim != 3))
         return NB_ERR_INVALID_ARGUMENT;
     if (dtype != NB_F32 && dtype != NB_F64) return NB_ERR_INVALID_ARGUMENT;
@@ -769,6 +777,18 @@ int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, 
     AccelArgs a{};
     a.src = (const char*)packed_src;
     a.n_chunks = nb_num_chunks(n_src, dtype);
+    if (window) {
+        // a window of the packed set [first, first + count), modulo ring_chunks when the window wraps (float modes only)
+        if (lut || want_phi || window->first_chunk < 0 || window->n_chunks <= 0 || window->splits_before < 0) return NB_ERR_INVALID_ARGUMENT;
+        const int64_t limit = window->ring_chunks > 0 ? window->ring_chunks : a.n_chunks;
+        if (window->ring_chunks > a.n_chunks || window->n_chunks > limit || (window->ring_chunks <= 0 && window->first_chunk + window->n_chunks > limit))
+            return NB_ERR_INVALID_ARGUMENT;
+        a.chunk0 = window->first_chunk;
+        a.n_chunks = window->n_chunks;
+        a.ring = window->ring_chunks > 0 ? window->ring_chunks : 0;
+        a.splits_before = window->splits_before;
+        a.max_splits = window->max_splits;
+    }
     a.pos_tgt = pos_tgt;
     a.n_tgt = n_tgt;
     a.partial = (double*)workspace;
@@ -828,7 +848,7 @@ int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, 
     if (rc != NB_OK) return rc;
     // what the reduction needs: Σ splits, ×G (float modes: G was hoisted out of the pair loop; LUT factors carry G)
     out->partial = a.partial;
-    out->splits = splits;
+    out->splits = splits + a.splits_before;
     out->count = n_tgt * dim;
     out->scale = lut ? (a.uniform_mass != 0.f ? (double)a.uniform_mass : 1.0) : (uni ? G * mass_value : G);
     out->out_f64 = dtype == NB_F64 || mode == NB_MODE_FLOAT64;
@@ -862,10 +882,11 @@ int nb::potential_from_phi(const PartialSums& p, int dtype, const void* mass_tgt
     return NB_OK;
 }
 
-extern "C" int nb_profile_next_force(void* start_event, void* stop_event) {
+extern "C" int nb_profile_next_force(void* start_event, void* stop_event, int launches) {
     ForceProfile& p = force_profile();
     p.start = start_event;
     p.stop = stop_event;
+    p.launches = launches < 1 ? 1 : launches;
     return NB_OK;
 }
 
@@ -887,9 +908,40 @@ extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_t
     if (!acc_out) return NB_ERR_INVALID_ARGUMENT;
     PartialSums p{};
     const int rc = accel_pairs(packed_src, n_src, pos_tgt, n_tgt, dim, dtype, mode, G, eps_sq, level_table, levels, uniform_mass,
-                               mass_value, scalars, workspace, workspace_bytes, (cudaStream_t)stream, &p, false);
+                               mass_value, scalars, workspace, workspace_bytes, (cudaStream_t)stream, &p, false, nullptr);
     if (rc != NB_OK) return rc;
     return accel_reduce(p, acc_out, scalars, (cudaStream_t)stream);
+}
+
+// Windowed evaluation (i-range-sharded ticks): the window of the rank's OWN packed slot runs while the all-gather of the
+// other slots is still in flight, then the ring window over the remaining slots; nb_accel_finish reduces both.
+extern "C" int nb_accel_window(const void* packed_src, int64_t n_src, int64_t first_chunk, int64_t n_chunks, int64_t ring_chunks,
+                               const void* pos_tgt, int64_t n_tgt, int dim, int dtype, int mode, double G, double eps_sq,
+                               int uniform_mass, double mass_value, void* workspace, int64_t workspace_bytes, int splits_before,
+                               int max_splits, int* splits_total_out, void* stream) {
+    if (!splits_total_out) return NB_ERR_INVALID_ARGUMENT;
+    PartialSums p{};
+    const SourceWindow w{first_chunk, n_chunks, ring_chunks, splits_before, max_splits};
+    const int rc = accel_pairs(packed_src, n_src, pos_tgt, n_tgt, dim, dtype, mode, G, eps_sq, nullptr, 0, uniform_mass, mass_value,
+                               nullptr, workspace, workspace_bytes, (cudaStream_t)stream, &p, false, &w);
+    if (rc != NB_OK) return rc;
+    *splits_total_out = p.splits;
+    return NB_OK;
+}
+
+extern "C" int nb_accel_finish(const void* workspace, int splits_total, int64_t n_tgt, int dim, int dtype, int mode, double G,
+                               int uniform_mass, double mass_value, void* acc_out, void* stream) {
+    if (!workspace || !acc_out || splits_total < 1 || n_tgt <= 0 || (dim != 2 && dim != 3)) return NB_ERR_INVALID_ARGUMENT;
+    if (mode != NB_MODE_FLOAT64 && mode != NB_MODE_FLOAT32 && mode != NB_MODE_FLOAT16 && mode != NB_MODE_BFLOAT16) return NB_ERR_UNSUPPORTED;
+    const bool uni = uniform_mass != 0 && ((dtype == NB_F32 && mode != NB_MODE_FLOAT64) || (dtype == NB_F64 && mode == NB_MODE_FLOAT64));
+    PartialSums p{};
+    p.partial = (const double*)workspace;
+    p.splits = splits_total;
+    p.count = n_tgt * dim;
+    p.scale = uni ? G * mass_value : G;
+    p.out_f64 = dtype == NB_F64 || mode == NB_MODE_FLOAT64;
+    p.minmax = false;
+    return accel_reduce(p, acc_out, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int nb_accel_potential(const void* packed_src, int64_t n_src, const void* pos_tgt, const void* mass_tgt, int64_t n_tgt,
@@ -899,7 +951,7 @@ extern "C" int nb_accel_potential(const void* packed_src, int64_t n_src, const v
     if (!acc_out || !pe_out || !mass_tgt) return NB_ERR_INVALID_ARGUMENT;
     PartialSums p{};
     int rc = accel_pairs(packed_src, n_src, pos_tgt, n_tgt, dim, dtype, mode, G, eps_sq, nullptr, 0, uniform_mass, mass_value,
-                         nullptr, workspace, workspace_bytes, (cudaStream_t)stream, &p, true);
+                         nullptr, workspace, workspace_bytes, (cudaStream_t)stream, &p, true, nullptr);
     if (rc != NB_OK) return rc;
     if ((rc = potential_from_phi(p, dtype, mass_tgt, mass_dtype, eps_sq, pe_out, (cudaStream_t)stream))) return rc;
     return accel_reduce(p, acc_out, nullptr, (cudaStream_t)stream);

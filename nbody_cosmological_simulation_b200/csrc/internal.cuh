@@ -20,10 +20,13 @@ struct PartialSums {
     int64_t n_tgt;
 };
 
+// a window of the packed source set: chunks [first_chunk, first_chunk + n_chunks), modulo ring_chunks when > 0
+struct SourceWindow { int64_t first_chunk, n_chunks, ring_chunks; int splits_before, max_splits; };
+
 int accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt, int dim, int dtype, int mode,
                 double G, double eps_sq, const void* level_table, int levels, int uniform_mass, double mass_value,
                 int64_t* scalars, void* workspace, int64_t workspace_bytes, cudaStream_t st, PartialSums* out,
-                bool want_phi = false);
+                bool want_phi = false, const SourceWindow* window = nullptr);
 // out[0] = Σ_{i<j} m_i m_j / r_ij (this shard's targets against all sources) from the potentials of a PHI pass
 int potential_from_phi(const PartialSums& p, int dtype, const void* mass_tgt, int mass_dtype, double eps_sq, double* out,
                        cudaStream_t st);

@@ -49,7 +49,9 @@ inline SplitPlan plan_splits(int64_t n_tgt, int64_t n_chunks, int targets_per_bl
         const double waves = ceil(ctas / slots);
         // useful work / capacity of the waves, each CTA paying ~0.2 chunk-equivalents of fixed cost
         const double eff = ((double)best.blocks_i * (double)n_chunks) / (waves * slots * ((double)cps + 0.2));
-        if (eff > best_eff * 1.01) { best_eff = eff; best.splits = (int)splits; best.chunks_per_split = (int)cps; }
+        // (a further split costs one more fp64 partial-sum slot — tens of MB written and read once, microseconds — which the
+        // fixed cost above already over-charges; r01 demanded a 1 % gain here and left 0.9 % on the table at N = 2^20)
+        if (eff > best_eff * 1.0005) { best_eff = eff; best.splits = (int)splits; best.chunks_per_split = (int)cps; }
     }
     if (best_eff < 0) { best.splits = 1; best.chunks_per_split = (int)n_chunks; }
     return best;

@@ -8,6 +8,8 @@ test (tests/fake_ops.py, built on the oracle) — the product never constructs a
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib as L
@@ -96,6 +98,36 @@ class CudaOps:
                                       float(eps_sq), L.ptr(table), int(levels or 0), int(bool(uniform[0])), float(uniform[1]),
                                       L.ptr(acc), L.ptr(scalars), L.ptr(ws),
                                       ws.numel(), L.stream_ptr(x_tgt.device)), "nb_accel")
+        return acc
+
+    def accel_workspace(self, x_tgt):
+        n, dim = x_tgt.shape
+        return self._scratch("accel", self.lib.nb_accel_workspace_bytes(n, dim), x_tgt.device)
+
+    def accel_window(self, packed, n_src, first_chunk, n_chunks, ring_chunks, x_tgt, mode: str, G, eps_sq, uniform=(False, 0.0),
+                     splits_before=0, max_splits=0) -> int:
+        """One window of a windowed force evaluation (nb_accel_window); returns the split slots used so far."""
+        L.require_cuda(packed, x_tgt)
+        n, dim = x_tgt.shape
+        ws = self._scratch("accel", self.lib.nb_accel_workspace_bytes(n, dim), x_tgt.device)
+        total = ctypes.c_int(0)
+        with torch.cuda.device(x_tgt.device):
+            L.check(self.lib.nb_accel_window(L.ptr(packed), int(n_src), int(first_chunk), int(n_chunks), int(ring_chunks),
+                                             L.ptr(x_tgt), n, dim, L.dtype_code(x_tgt), L.MODE_CODES[mode], float(G), float(eps_sq),
+                                             int(bool(uniform[0])), float(uniform[1]), L.ptr(ws), ws.numel(), int(splits_before),
+                                             int(max_splits), ctypes.byref(total), L.stream_ptr(x_tgt.device)), "nb_accel_window")
+        return total.value
+
+    def accel_finish(self, splits_total, x_tgt, mode: str, G, uniform=(False, 0.0)):
+        n, dim = x_tgt.shape
+        code = L.dtype_code(x_tgt)
+        out_dtype = torch.float64 if (code == L.NB_F64 or mode == "float64") else torch.float32
+        acc = torch.empty((n, dim), dtype=out_dtype, device=x_tgt.device)
+        ws = self._scratch("accel", self.lib.nb_accel_workspace_bytes(n, dim), x_tgt.device)
+        with torch.cuda.device(x_tgt.device):
+            L.check(self.lib.nb_accel_finish(L.ptr(ws), int(splits_total), n, dim, code, L.MODE_CODES[mode], float(G),
+                                             int(bool(uniform[0])), float(uniform[1]), L.ptr(acc), L.stream_ptr(x_tgt.device)),
+                    "nb_accel_finish")
         return acc
 
     def accel_potential(self, packed, n_src, x_tgt, m_tgt, mode: str, G, eps_sq, uniform=(False, 0.0)):

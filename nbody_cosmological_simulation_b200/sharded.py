@@ -4,11 +4,13 @@ One process per GPU (`torch.distributed`, NCCL over NVLink 5 / NVSwitch).  Each 
 positions/velocities/accelerations of a contiguous, chunk-aligned slice of the particles
 (SURVEY.md §8e).  A tick is
 
-    fused KDK on the local slice           -> new local x, v  + the local PACKED source records
-    all_gather_into_tensor(packed)         -> full source set on every rank (N·16 B fp32, N·32 B fp64)
-    [int modes: local max d² -> all_reduce(MAX) -> level table]
-    force kernel: local targets × all sources
-    [INT8/INT4: all_reduce(MIN/MAX) of the local acceleration extrema -> shared snap grid]
+    fused KDK on the local slice           -> new local x, v  + the local PACKED source records, written straight
+                                              into this rank's slot of the gathered buffer
+    all_gather_into_tensor (in place)      -> full source set on every rank (N·16 B fp32, N·32 B fp64) — on a side
+                                              stream, WHILE the force kernel already runs on the rank's own slot
+    force kernel, window 1: local targets × own slot;  window 2 (after the gather): × the other P−1 slots, ring order
+    [int modes need the global max d² before any pair can be formed: gather -> local max d² -> all_reduce(MAX) ->
+     level table -> one force launch; INT8/INT4: all_reduce(MIN/MAX) of the acceleration extrema -> shared snap grid]
 
 No other data-path collective exists; energies add one all_reduce(SUM) of a double.  The arithmetic
 per pair is the single-GPU kernel's, so results are identical to `GalaxySimulation` up to the
@@ -18,6 +20,8 @@ from __future__ import annotations
 
 from typing import Callable, Optional
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -26,6 +30,8 @@ from . import _lib as L
 from .quantization import PrecisionMode, levels_for_mode
 
 _INT_FORCE_SNAP = {PrecisionMode.INT8_SIM: 256, PrecisionMode.INT4_SIM: 16}
+_OVERLAP = os.environ.get("NB_B200_OVERLAP", "1") != "0"       # all-gather hidden behind the own-slot force window
+_WINDOW_MODES = (PrecisionMode.FLOAT64, PrecisionMode.FLOAT32, PrecisionMode.FLOAT16, PrecisionMode.BFLOAT16)
 
 
 class ShardPlan:
@@ -93,6 +99,7 @@ class ShardedGalaxySimulation:
             return local_packed
         if self._packed_all is None or self._packed_all.numel() != local_packed.numel() * self.world:
             self._packed_all = torch.empty(local_packed.numel() * self.world, dtype=torch.uint8, device=self.device)
+        # on CUDA local_packed IS this rank's slot of _packed_all: NCCL gathers in place
         dist.all_gather_into_tensor(self._packed_all, local_packed, group=self.group)
         return self._packed_all
 
@@ -116,14 +123,32 @@ class ShardedGalaxySimulation:
         return self.plan
 
     def _local_packed_buffer(self, dtype) -> torch.Tensor:
+        """Where the KDK / pack kernel writes this rank's packed records: its own slot of the gathered buffer (NCCL
+        gathers in place), or a separate buffer on CPU test backends."""
         plan = self._plan_for(dtype)
         nbytes = plan.slot_chunks * self.ops.chunk_bytes(self.dim)
+        if self.world > 1 and self.device.type == "cuda":
+            if self._packed_all is None or self._packed_all.numel() != nbytes * self.world:
+                self._packed_all = torch.empty(nbytes * self.world, dtype=torch.uint8, device=self.device)
+            return self._packed_all[self.rank * nbytes:(self.rank + 1) * nbytes]
         key = "_lp%d" % nbytes
         buf = getattr(self, key, None)
         if buf is None:
             buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             setattr(self, key, buf)
         return buf
+
+    def _side_stream(self):
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        return self._comm_stream
+
+    def pair_launches_next_tick(self) -> int:
+        """How many pair-kernel launches the next tick's force evaluation makes (instrumentation: _lib.ForceTimer.arm)."""
+        x = self.positions
+        windowed = self.world > 1 and _OVERLAP and self.precision_mode in _WINDOW_MODES and \
+            not (getattr(self, "_pe_wanted", False) and self._pe_fusable_dtype(torch.promote_types(x.dtype, self.accelerations.dtype)))
+        return 2 if windowed else 1
 
     def _force(self, x: torch.Tensor, emit: bool, local_packed: Optional[torch.Tensor] = None,
                want_pe: bool = False) -> torch.Tensor:
@@ -133,18 +158,20 @@ class ShardedGalaxySimulation:
         if emit:
             local_packed = self._local_packed_buffer(x.dtype)
             ops.pack(x, self.masses, local_packed, plan.slot_chunks)
-        packed = self._all_gather_packed(local_packed)
-        self._last_packed, self._last_nsrc = packed, plan.padded_sources if self.world > 1 else plan.slot_chunks * plan.chunk_sources
-        n_src = self._last_nsrc
         mode = self.precision_mode
         levels = levels_for_mode(mode) or 0
+        n_src = plan.padded_sources if self.world > 1 else plan.slot_chunks * plan.chunk_sources
+        self._pe_local = None
+        if self.world > 1 and _OVERLAP and mode in _WINDOW_MODES and not (want_pe and self._pe_fusable(x)):
+            return self._force_windowed(x, local_packed, plan, n_src)
+        packed = self._all_gather_packed(local_packed)
+        self._last_packed, self._last_nsrc = packed, n_src
         table = None
         if levels:
             ops.reset_scalars(self.scalars)
             ops.max_dist_sq(packed, n_src, x, self.softening_sq, self.scalars)
             self._all_reduce(self.scalars[L.SLOT_MAX_D2:L.SLOT_MAX_D2 + 1], dist.ReduceOp.MAX)
             table = ops.build_level_table(self.scalars, x.dtype, self.softening_sq, 0.01, self.G, levels)
-        self._pe_local = None
         if want_pe and self._pe_fusable(x):
             acc, pe = ops.accel_potential(packed, n_src, x, self.masses, mode.value, self.G, self.softening_sq,
                                           uniform=self._uniform_mass())
@@ -157,10 +184,42 @@ class ShardedGalaxySimulation:
             self._all_reduce(self.scalars[L.SLOT_ACC_MAX:L.SLOT_ACC_MAX + 1], dist.ReduceOp.MAX)
         return acc
 
-    def _pe_fusable(self, x) -> bool:
+    def _force_windowed(self, x, local_packed, plan, n_src):
+        """Float modes on several ranks.  Compute stream: the pair kernel over this rank's OWN slot (1/P of the work)
+        starts at once.  Side stream: the in-place all-gather of the other slots, then the pair kernel over those P−1
+        slots in ring order.  The two launches run concurrently (the hardware fills the tail of one with the other); one
+        reduction over the split slots of both follows on the compute stream."""
+        ops, mode, uni = self.ops, self.precision_mode.value, self._uniform_mass()
+        slot = plan.slot_chunks
+        first, rest = (self.rank * slot, slot, 0), ((self.rank + 1) * slot, (self.world - 1) * slot, self.world * slot)
+        if not x.is_cuda:                        # CPU test backends: same windows, no streams
+            packed = self._all_gather_packed(local_packed)
+            self._last_packed, self._last_nsrc = packed, n_src
+            used = ops.accel_window(packed, n_src, *first, x, mode, self.G, self.softening_sq, uniform=uni, splits_before=0, max_splits=6)
+            used = ops.accel_window(packed, n_src, *rest, x, mode, self.G, self.softening_sq, uniform=uni, splits_before=used)
+            return ops.accel_finish(used, x, mode, self.G, uniform=uni)
+        main, side = torch.cuda.current_stream(self.device), self._side_stream()
+        packed = self._packed_all
+        self._last_packed, self._last_nsrc = packed, n_src
+        ops.accel_workspace(x)                   # allocate the shared scratch on the compute stream before either launch
+        ready = torch.cuda.Event()
+        ready.record(main)                       # the KDK kernel has written this rank's slot
+        used = ops.accel_window(packed, n_src, *first, x, mode, self.G, self.softening_sq, uniform=uni, splits_before=0, max_splits=6)
+        done = torch.cuda.Event()
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            self._all_gather_packed(local_packed)
+            used = ops.accel_window(packed, n_src, *rest, x, mode, self.G, self.softening_sq, uniform=uni, splits_before=used)
+            done.record(side)
+        main.wait_event(done)
+        return ops.accel_finish(used, x, mode, self.G, uniform=uni)
+
+    def _pe_fusable_dtype(self, dtype) -> bool:
         mode = self.precision_mode
-        return (mode == PrecisionMode.FLOAT32 and x.dtype == torch.float32) or \
-               (mode == PrecisionMode.FLOAT64 and x.dtype == torch.float64)
+        return (mode == PrecisionMode.FLOAT32 and dtype == torch.float32) or (mode == PrecisionMode.FLOAT64 and dtype == torch.float64)
+
+    def _pe_fusable(self, x) -> bool:
+        return self._pe_fusable_dtype(x.dtype)
 
     def _uniform_mass(self):
         """(all masses equal on every rank, value): local min/max, all-reduced; cached per masses tensor version."""

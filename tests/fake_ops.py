@@ -153,6 +153,29 @@ class FakeOps:
             scalars[L.SLOT_ACC_MAX] = max(int(scalars[L.SLOT_ACC_MAX]), key(acc.max().item()))
         return acc
 
+    def accel_window(self, packed, n_src, first_chunk, n_chunks, ring_chunks, x_tgt, mode, G, eps_sq, uniform=(False, 0.0),
+                     splits_before=0, max_splits=0):
+        """Partial accelerations of one source window (chunks taken modulo ring_chunks when > 0), kept per slot."""
+        cs = self.chunk_sources(x_tgt.dtype)
+        pos, m = self.unpack(packed, n_src, x_tgt.shape[1], x_tgt.dtype)
+        idx = torch.arange(first_chunk, first_chunk + n_chunks)
+        if ring_chunks > 0:
+            idx = idx % ring_chunks
+        sel = (idx.unsqueeze(1) * cs + torch.arange(cs).unsqueeze(0)).reshape(-1)
+        diff = pos[sel].unsqueeze(0) - x_tgt.unsqueeze(1)
+        d2 = (diff ** 2).sum(dim=-1) + eps_sq
+        u = ora.quantize_distance_squared(d2, mode)
+        part = ((1.0 / (u ** 1.5) * m[sel].unsqueeze(0)).unsqueeze(-1) * diff).sum(dim=1)
+        if splits_before == 0:
+            self._window_parts = []
+        self._window_parts.append(part.double())
+        return splits_before + 1
+
+    def accel_finish(self, splits_total, x_tgt, mode, G, uniform=(False, 0.0)):
+        assert splits_total == len(self._window_parts)
+        tot = sum(self._window_parts) * G
+        return tot if (mode == "float64" or x_tgt.dtype == torch.float64) else tot.to(torch.float32)
+
     def accel_potential(self, packed, n_src, x_tgt, m_tgt, mode, G, eps_sq, uniform=(False, 0.0)):
         acc = self.accel(packed, n_src, x_tgt, mode, G, eps_sq, None, 0, None)
         return acc, self.potential(packed, n_src, x_tgt, m_tgt, eps_sq)

@@ -45,5 +45,8 @@ def test_c2_sized_sweep_runs_unchanged(tmp_path):
         e = s[mode]["energy"]
         assert abs(e[0] - e64[0]) <= 3e-6 * abs(e64[0])                  # same initial state in every mode
         drift = abs(e[-1] - e[0]) / abs(e[0])
-        assert drift < (0.05 if mode == "int4_sim" else 2e-3 if mode == "int8_sim" else 1e-4), (mode, drift)
+        # leapfrog at dt = 0.01 itself drifts ~1.2e-4 here (float64: 1.23e-4 measured); the float modes must sit on that curve
+        assert drift < (0.05 if mode == "int4_sim" else 2e-3 if mode == "int8_sim" else 3e-4), (mode, drift)
+        if mode in ("float32", "float16"):
+            assert abs(e[-1] - e64[-1]) <= 2e-5 * abs(e64[-1]), (mode, e[-1], e64[-1])
     assert s["override_vs_custom_rel"] < 1e-5

@@ -18,7 +18,7 @@
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e_)); exit(1);} } while (0)
 
 constexpr int ILP = 8;
-constexpr int ITERS = 4096;
+constexpr int ITERS = 32768;     // ~1-10 ms per kernel: launch ramp and tail are < 1 % of the time
 constexpr int UNROLL = 16;
 
 struct Result { unsigned long long cycles; };
