@@ -60,12 +60,25 @@ class ShardPlan:
 
 
 class ShardedGalaxySimulation:
-    """`GalaxySimulation` semantics on P ranks.  Every rank passes the same full initial arrays (same seed or
-    broadcast beforehand); `positions`/`velocities`/`accelerations`/`masses` hold the LOCAL slice."""
+    """`GalaxySimulation` semantics on P ranks; `positions`/`velocities`/`accelerations`/`masses` hold the LOCAL slice.
+
+    Two ways to hand over the initial state: every rank passes the same FULL arrays (same seed or broadcast beforehand)
+    and the engine keeps its slice — or, with `num_stars=N`, every rank passes only ITS OWN slice of an N-star system
+    (`ShardedGalaxySimulation.plan_for(N, dtype).slice(rank)`; e.g. from galaxy.create_disk_galaxy_sharded), so that no
+    rank ever holds the whole system."""
+
+    @staticmethod
+    def plan_for(num_stars: int, dtype=torch.float32, group=None, ops=None) -> "ShardPlan":
+        """The i-range partition the engine will use for `num_stars` stars of `dtype` on the current process group."""
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        chunk = 256 if dtype == torch.float32 else 128
+        if ops is not None:
+            chunk = ops.chunk_sources(dtype)
+        return ShardPlan(num_stars, world, chunk)
 
     def __init__(self, positions: torch.Tensor, velocities: torch.Tensor, masses: torch.Tensor,
                  precision_mode: PrecisionMode = PrecisionMode.FLOAT64, G: float = 0.001, softening: float = 0.1,
-                 dt: float = 0.01, device: torch.device = None, group=None, ops=None):
+                 dt: float = 0.01, device: torch.device = None, group=None, ops=None, num_stars: int = None):
         if ops is None:
             from .ops import CudaOps
             ops = CudaOps()
@@ -76,7 +89,8 @@ class ShardedGalaxySimulation:
         self.device = torch.device(device) if device is not None else positions.device
         self.precision_mode = precision_mode
         self.G, self.softening, self.softening_sq, self.dt = G, softening, softening ** 2, dt
-        self.num_stars = len(masses)
+        local_input = num_stars is not None
+        self.num_stars = int(num_stars) if local_input else len(masses)
         self.dim = positions.shape[1]
 
         # dtype of the state: FLOAT64 mode promotes fp32 state to fp64 after the first kick (Appendix A);
@@ -84,6 +98,10 @@ class ShardedGalaxySimulation:
         # for the very first force evaluation only.
         self.plan = ShardPlan(self.num_stars, self.world, ops.chunk_sources(positions.dtype))
         sl = self.plan.slice(self.rank)
+        if local_input:
+            if len(masses) != self.plan.count[self.rank]:
+                raise ValueError(f"rank {self.rank} owns stars [{sl.start}, {sl.stop}) of {self.num_stars}; got {len(masses)} rows")
+            sl = slice(None)
         self.positions = positions[sl].clone().to(self.device).contiguous()
         self.velocities = velocities[sl].clone().to(self.device).contiguous()
         self.masses = masses[sl].clone().to(self.device).contiguous()
