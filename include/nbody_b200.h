@@ -208,8 +208,10 @@ int nb_kdk(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_o
  * its attributes to new tensors every tick: giving fresh x, v, acc buffers reproduces that without copies.  Per tick: nb_kdk(KICK_KICK_DRIFT, emitting `packed`) -> [int modes: nb_reset_scalars, nb_max_dist_sq,
  * nb_build_level_table] -> nb_accel; a closing nb_kdk(KICK) leaves a consistent, observable state.  Bit-identical
  * to issuing those calls one by one.  levels = d² grid levels (0 for float modes), snap_levels = force grid levels
- * (INT8/INT4, else 0).  use_graph != 0 captures the tick body once into a CUDA graph and replays it (worth it for
- * small systems where launch latency dominates).  packed: nb_packed_bytes; level_table: nb_level_table_bytes (or
+ * (INT8/INT4, else 0).  use_graph = 1 captures the tick body once into a CUDA graph and replays it (worth it for
+ * small systems where launch latency dominates); use_graph = 2 additionally runs the steady-state ticks of small fp32
+ * systems in FLOAT32 mode (n <= 32768) as ONE persistent cooperative kernel with grid-wide barriers between the
+ * integrator and force phases, falling back to the graph when the grid cannot be co-resident.  packed: nb_packed_bytes; level_table: nb_level_table_bytes (or
  * NULL); workspace: max(nb_accel_workspace_bytes, nb_max_dist_workspace_bytes) — the two uses never overlap.
  * pe_out (device double[1], may be NULL): when given, the force pass of the LAST tick also accumulates Σ_j m_j / r_ij
  * per target (one more packed op per source pair) and pe_out[0] receives Σ_{i<j} m_i m_j / r_ij of the final

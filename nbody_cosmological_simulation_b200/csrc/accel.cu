@@ -11,6 +11,7 @@
 // accumulators per chunk => the Σ_j error does not grow with N (SURVEY.md §7 "hard parts").
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
+#include <cooperative_groups.h>
 #include "stream.cuh"
 #include "lut.cuh"
 #include "internal.cuh"
@@ -53,7 +54,10 @@ struct AccelArgs {
     float uniform_mass;       // Q_LUTF: != 0 when every real source has this mass (the per-pair mass multiply is dropped)
     int splits_before;        // windowed evaluation: split slots already used by earlier windows
     int max_splits;           // > 0: cap on the split count of this launch
+    int tile, split;          // persistent whole-tick kernel: this CTA's task (target tile, source split) + 1; 0 = blockIdx.x / .y
 };
+__device__ __forceinline__ int tile_of(const AccelArgs& a) { return a.tile ? a.tile - 1 : (int)blockIdx.x; }
+__device__ __forceinline__ int split_of(const AccelArgs& a) { return a.split ? a.split - 1 : (int)blockIdx.y; }
 
 // Level table layout (Q_LUT): float4 entry[k] = { T_{k+1}, g_k, g_{k+1}, 0 } for k = 0..L-1, preceded by a
 // 16-byte header { lo2 (log2 of lower bound), scale (levels-1)/(hi2-lo2), min_val, degenerate flag }
@@ -100,7 +104,7 @@ struct ForceF32 {
         const float* pos = reinterpret_cast<const float*>(a.pos_tgt);
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
-            int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            int64_t i = (int64_t)tile_of(a) * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i >= a.n_tgt) i = a.n_tgt - 1;
             const float x = pos[i * DIM + 0], y = pos[i * DIM + 1], z = DIM == 3 ? pos[i * DIM + 2] : 0.f;
             nx[t] = make_float2(-x, -x); ny[t] = make_float2(-y, -y); nz[t] = make_float2(-z, -z);
@@ -386,14 +390,14 @@ struct ForceF32 {
     }
 
     __device__ __forceinline__ void store(const AccelArgs& a) const {
-        double* out = a.partial + (int64_t)blockIdx.y * a.n_tgt * DIM;
+        double* out = a.partial + (int64_t)split_of(a) * a.n_tgt * DIM;
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
-            const int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            const int64_t i = (int64_t)tile_of(a) * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i < a.n_tgt) {
                 out[i * DIM + 0] = sx[t]; out[i * DIM + 1] = sy[t];
                 if (DIM == 3) out[i * DIM + 2] = sz[t];
-                if (PHI) a.partial_phi[(int64_t)blockIdx.y * a.n_tgt + i] = sp[t];
+                if (PHI) a.partial_phi[(int64_t)split_of(a) * a.n_tgt + i] = sp[t];
             }
         }
     }
@@ -441,7 +445,7 @@ struct ForceF64 {
         const double* pos = reinterpret_cast<const double*>(a.pos_tgt);
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
-            int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            int64_t i = (int64_t)tile_of(a) * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i >= a.n_tgt) i = a.n_tgt - 1;
             xi[t] = pos[i * DIM + 0]; yi[t] = pos[i * DIM + 1]; zi[t] = DIM == 3 ? pos[i * DIM + 2] : 0.0;
             sx[t] = sy[t] = sz[t] = 0.0;
@@ -517,14 +521,14 @@ struct ForceF64 {
         }
     }
     __device__ __forceinline__ void store(const AccelArgs& a) const {
-        double* out = a.partial + (int64_t)blockIdx.y * a.n_tgt * DIM;
+        double* out = a.partial + (int64_t)split_of(a) * a.n_tgt * DIM;
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
-            const int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            const int64_t i = (int64_t)tile_of(a) * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i < a.n_tgt) {
                 out[i * DIM + 0] = sx[t]; out[i * DIM + 1] = sy[t];
                 if (DIM == 3) out[i * DIM + 2] = sz[t];
-                if (PHI) a.partial_phi[(int64_t)blockIdx.y * a.n_tgt + i] = sp[t];
+                if (PHI) a.partial_phi[(int64_t)split_of(a) * a.n_tgt + i] = sp[t];
             }
         }
     }
@@ -544,7 +548,7 @@ struct ForceMixed {       // fp32 sources/targets, FLOAT64 mode
         const float* pos = reinterpret_cast<const float*>(a.pos_tgt);
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
-            int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            int64_t i = (int64_t)tile_of(a) * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i >= a.n_tgt) i = a.n_tgt - 1;
             xi[t] = pos[i * DIM + 0]; yi[t] = pos[i * DIM + 1]; zi[t] = DIM == 3 ? pos[i * DIM + 2] : 0.f;
             sx[t] = sy[t] = sz[t] = 0.0;
@@ -580,10 +584,10 @@ struct ForceMixed {       // fp32 sources/targets, FLOAT64 mode
         }
     }
     __device__ __forceinline__ void store(const AccelArgs& a) const {
-        double* out = a.partial + (int64_t)blockIdx.y * a.n_tgt * DIM;
+        double* out = a.partial + (int64_t)split_of(a) * a.n_tgt * DIM;
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
-            const int64_t i = (int64_t)blockIdx.x * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            const int64_t i = (int64_t)tile_of(a) * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i < a.n_tgt) {
                 out[i * DIM + 0] = sx[t]; out[i * DIM + 1] = sy[t];
                 if (DIM == 3) out[i * DIM + 2] = sz[t];
@@ -692,6 +696,101 @@ __global__ void __launch_bounds__(1024) phi_final_kernel(const double* __restric
     for (int e = threadIdx.x; e < count; e += blockDim.x) s += partials[e];
     s = block_reduce(s, OpAdd(), 0.0, red);
     if (threadIdx.x == 0) out[0] = 0.5 * s;
+}
+
+// ======================================================================================================
+// Persistent whole-tick kernel for small systems (N <= ~16K): GalaxySimulation.run, simulation.py:145-158
+// ======================================================================================================
+// At N <= 10^4 a tick is a few microseconds of arithmetic; launched as two kernels per tick (even replayed from a CUDA
+// graph) it costs 13-16 us, most of it launch gaps and kernel ramp.  Here ONE cooperative launch runs `ticks` ticks: all
+// CTAs stay resident and alternate between
+//   phase 1 (every thread, grid-stride over particle pairs): reduce the j-split partial sums of the previous force pass,
+//           closing kick + opening kick + drift with separately rounded mul/add, write x, v, a and the packed records;
+//   phase 2 (CTA = one task: a tile of targets x a range of source chunks): the pair loop of accel_kernel, same consumer,
+//           same TMA ring, leaving partial sums;
+// separated by grid-wide barriers.  The arithmetic per value is that of kdk_kernel / accel_kernel (integrate.cu), so a
+// run is bit-identical to issuing the kernels one by one.  cudaLaunchCooperativeKernel refuses a grid that is not
+// co-resident, so the barriers cannot deadlock; the host falls back to the graph replay when it refuses.
+struct PersistentArgs {
+    AccelArgs a;                 // chunks_per_split / partial / n_tgt ... of the in-kernel force passes
+    float* x; float* v; float* acc; const void* mass; int mass_f64;
+    int64_t n, n_units; float half_dt, dt; char* packed;
+    int ticks, tiles, splits;    // tasks = tiles x splits (<= gridDim.x)
+    double scale;                // G or G*m (uniform masses)
+    const double* partial_in; int splits_in;     // partial sums left by the force pass that preceded the launch
+};
+
+template <int DIM>
+__device__ __forceinline__ void persistent_kdk(const PersistentArgs& p, const double* partial, int splits) {
+    const int64_t count = p.n * DIM;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t unit = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; unit < p.n_units; unit += stride) {
+        float px[2][3], pm[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t i = unit * 2 + h;
+            if (i < p.n) {
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) {
+                    const int64_t e = i * DIM + k;
+                    double s = 0.0;
+                    for (int sp = 0; sp < splits; ++sp) s += partial[(int64_t)sp * count + e];        // split order, as accel_finalize
+                    const float a = (float)(s * p.scale);
+                    p.acc[e] = a;
+                    const float kick = __fmul_rn(a, p.half_dt);
+                    float v = __fadd_rn(p.v[e], kick);                        // simulation.py:141 (closing kick)
+                    v = __fadd_rn(v, kick);                                   // :132 (opening kick of the next tick)
+                    p.v[e] = v;
+                    const float x = __fadd_rn(p.x[e], __fmul_rn(v, p.dt));    // :135
+                    p.x[e] = x;
+                    px[h][k] = x;
+                }
+                pm[h] = p.mass_f64 ? (float)reinterpret_cast<const double*>(p.mass)[i] : reinterpret_cast<const float*>(p.mass)[i];
+            } else {
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) px[h][k] = kPadCoordF32;         // padding record: far away, mass 0
+                pm[h] = 0.f;
+            }
+        }
+        const int64_t chunk = unit / kChunkUnits;
+        const int u = (int)(unit % kChunkUnits);
+        char* base = p.packed + chunk * (int64_t)chunk_bytes(DIM);
+        *reinterpret_cast<float4*>(base + u * 16) = make_float4(px[0][0], px[1][0], px[0][1], px[1][1]);
+        if (DIM == 3) *reinterpret_cast<float4*>(base + kChunkABytes + u * 16) = make_float4(px[0][2], px[1][2], pm[0], pm[1]);
+        else          *reinterpret_cast<float2*>(base + kChunkABytes + u * 8) = make_float2(pm[0], pm[1]);
+    }
+}
+
+template <class Consumer>
+__global__ void __launch_bounds__(Consumer::THREADS + 32, 2) persistent_ticks_kernel(const PersistentArgs p) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const bool is_consumer = threadIdx.x < Consumer::THREADS;
+    const int tasks = p.tiles * p.splits;
+    AccelArgs a = p.a;
+    a.tile = (int)(blockIdx.x % p.tiles) + 1;
+    a.split = (int)(blockIdx.x / p.tiles) + 1;
+    const double* partial = p.partial_in;
+    int splits = p.splits_in;
+    for (int t = 0; t < p.ticks; ++t) {
+        persistent_kdk<Consumer::DIM>(p, partial, splits);
+        __threadfence();
+        grid.sync();
+        // the packed records were written through the generic proxy; the TMA engine reads them through the async proxy
+        asm volatile("fence.proxy.async;" ::: "memory");
+        if ((int)blockIdx.x < tasks) {
+            Consumer cons;
+            if (is_consumer) cons.init(a, nullptr);
+            const int64_t c0 = (int64_t)(a.split - 1) * a.chunks_per_split;
+            const int64_t c1 = min(a.n_chunks, c0 + (int64_t)a.chunks_per_split);
+            stream_sources(a.src, c0, c1, cons);
+            if (is_consumer) cons.store(a);
+        }
+        __threadfence();
+        grid.sync();
+        partial = a.partial;
+        splits = p.splits;
+    }
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
@@ -879,6 +978,83 @@ int nb::potential_from_phi(const PartialSums& p, int dtype, const void* mass_tgt
     NB_CUDA_LAUNCH_CHECK();
     phi_final_kernel<<<1, 1024, 0, st>>>(blocks, (int)nb, out);
     NB_CUDA_LAUNCH_CHECK();
+    return NB_OK;
+}
+
+// `ticks` steady-state ticks (closing kick of the previous tick fused with kick-drift, then the force) in ONE cooperative
+// launch; `ps` describes the partial sums of the force pass before the launch on entry and those of the last in-kernel
+// pass on return.  NB_ERR_UNSUPPORTED when the configuration is outside the kernel's scope or the grid cannot be
+// co-resident — the caller then replays the tick body from a CUDA graph instead.
+template <class Consumer>
+static int launch_persistent(PersistentArgs& p, int64_t workspace_bytes, cudaStream_t st, int* splits_out) {
+    auto kern = persistent_ticks_kernel<Consumer>;
+    const int threads = Consumer::THREADS + 32;
+    const int smem = stream_smem_bytes(Consumer::DIM);
+    int occ = 0;
+    const int frc = kernel_occupancy((const void*)kern, threads, smem, &occ);
+    if (frc != NB_OK) return frc;
+    const int cap = device_sm_count() * occ;
+    const int tpb = Consumer::THREADS * Consumer::TARGETS_PER_THREAD;
+    const int tiles = (int)((p.n + tpb - 1) / tpb);
+    if (tiles > cap) return NB_ERR_UNSUPPORTED;
+    int64_t max_splits = cap / tiles;
+    const int64_t per_split = p.n * Consumer::DIM * (int64_t)sizeof(double);
+    if (max_splits > workspace_bytes / per_split) max_splits = workspace_bytes / per_split;
+    if (max_splits > max_splits_for(p.n, Consumer::DIM)) max_splits = max_splits_for(p.n, Consumer::DIM);
+    if (max_splits > p.a.n_chunks) max_splits = p.a.n_chunks;
+    if (max_splits < 1) return NB_ERR_WORKSPACE_TOO_SMALL;
+    const int cps = (int)((p.a.n_chunks + max_splits - 1) / max_splits);
+    const int splits = (int)((p.a.n_chunks + cps - 1) / cps);
+    p.a.chunks_per_split = cps;
+    p.tiles = tiles;
+    p.splits = splits;
+    // every SM takes part in the elementwise phase even when there are fewer tasks than SMs
+    int grid = tiles * splits;
+    if (grid < device_sm_count()) grid = device_sm_count();
+    void* params[] = {(void*)&p};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(threads), params, (size_t)smem, st);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources) {
+        cudaGetLastError();
+        return NB_ERR_UNSUPPORTED;
+    }
+    if (e != cudaSuccess) return cuda_status(e);
+    *splits_out = splits;
+    return NB_OK;
+}
+
+int nb::persistent_ticks(void* x, void* v, void* acc, const void* mass, int mass_dtype, int64_t n, int dim, int dtype, int mode, double G,
+                         double eps_sq, double dt, int uniform_mass, double mass_value, void* packed, void* workspace,
+                         int64_t workspace_bytes, int64_t ticks, PartialSums* ps, cudaStream_t st) {
+    if (dtype != NB_F32 || mode != NB_MODE_FLOAT32 || ticks < 1 || ticks > 0x7fffffff || n > 32768 || !ps || !ps->partial ||
+        ps->out_f64 || ps->minmax)
+        return NB_ERR_UNSUPPORTED;
+    const bool uni = uniform_mass != 0;
+    PersistentArgs p{};
+    p.a.src = (const char*)packed;
+    p.a.n_chunks = nb_num_chunks(n, dtype);
+    p.a.pos_tgt = x;
+    p.a.n_tgt = n;
+    p.a.partial = (double*)workspace;
+    p.a.eps_sq = eps_sq;
+    p.a.neg_zero = -0.0f;
+    p.x = (float*)x; p.v = (float*)v; p.acc = (float*)acc; p.mass = mass; p.mass_f64 = mass_dtype == NB_F64;
+    p.n = n; p.n_units = p.a.n_chunks * kChunkUnits;
+    p.half_dt = (float)(dt / 2); p.dt = (float)dt;
+    p.packed = (char*)packed;
+    p.ticks = (int)ticks;
+    p.scale = uni ? G * mass_value : G;
+    p.partial_in = ps->partial; p.splits_in = ps->splits;
+    if (ps->scale != p.scale || ps->count != n * dim) return NB_ERR_UNSUPPORTED;
+    int splits = 0, rc;
+    // few targets: one target per thread doubles the number of tiles (shorter tasks, more SMs busy)
+    const bool small = (n + 511) / 512 * p.a.n_chunks <= device_sm_count();
+#define NB_PERSIST(D, U, I) rc = launch_persistent<ForceF32<D, Q_F32, I, kForceThreads, U>>(p, workspace_bytes, st, &splits)
+    if (dim == 2) { if (uni) { if (small) NB_PERSIST(2, true, 1); else NB_PERSIST(2, true, 2); } else { if (small) NB_PERSIST(2, false, 1); else NB_PERSIST(2, false, 2); } }
+    else          { if (uni) { if (small) NB_PERSIST(3, true, 1); else NB_PERSIST(3, true, 2); } else { if (small) NB_PERSIST(3, false, 1); else NB_PERSIST(3, false, 2); } }
+#undef NB_PERSIST
+    if (rc != NB_OK) return rc;
+    ps->partial = (const double*)workspace;
+    ps->splits = splits;
     return NB_OK;
 }
 

@@ -32,6 +32,11 @@ int potential_from_phi(const PartialSums& p, int dtype, const void* mass_tgt, in
                        cudaStream_t st);
 int accel_reduce(const PartialSums& p, void* acc_out, int64_t* scalars, cudaStream_t st);
 
+// `ticks` steady-state ticks of a small fp32 system in ONE cooperative launch (accel.cu); NB_ERR_UNSUPPORTED when out of scope
+int persistent_ticks(void* x, void* v, void* acc, const void* mass, int mass_dtype, int64_t n, int dim, int dtype, int mode, double G,
+                     double eps_sq, double dt, int uniform_mass, double mass_value, void* packed, void* workspace,
+                     int64_t workspace_bytes, int64_t ticks, PartialSums* ps, cudaStream_t st);
+
 // nb_kdk with the accelerations taken from j-split partial sums (reduced on the fly, written to `acc` as well)
 int kdk_from_partials(const void* x_in, const void* v_in, void* acc, void* x_out, void* v_out, int64_t n, int dim, int dtype,
                       double dt, int phase, const int64_t* scalars, const void* mass, int mass_dtype, void* packed_out,

@@ -76,6 +76,13 @@ extern "C" int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_
     if (rc) return rc;
     int64_t remaining = ticks - 1;
     const int64_t tail = pe_out ? 1 : 0;                    // the last tick is enqueued directly when it carries the potential
+    if (use_graph >= 2 && deferred && remaining - tail >= 2) {
+        // small fp32 systems: all remaining ticks in ONE cooperative launch (grid barriers instead of launches)
+        rc = persistent_ticks(x, v, acc, mass, mass_dtype, n, dim, dtype, mode, G, eps_sq, dt, uniform_mass, mass_value, packed, workspace,
+                              workspace_bytes, remaining - tail, &ps, st);
+        if (rc == NB_OK) remaining = tail;
+        else if (rc != NB_ERR_UNSUPPORTED) return rc;       // unsupported / not co-resident: graph replay below
+    }
     if (use_graph && remaining - tail >= 4) {
         // capture one steady-state tick on a private stream (the caller's may be the legacy default stream, which
         // cannot be captured), then replay it on the caller's stream

@@ -7,6 +7,7 @@
 // kStages-1 stages, so there is no CTA-wide barrier in the steady state.
 #pragma once
 #include <math.h>
+#include <stdlib.h>
 #include <mutex>
 #include "common.cuh"
 
@@ -54,6 +55,12 @@ inline SplitPlan plan_splits(int64_t n_tgt, int64_t n_chunks, int targets_per_bl
         if (eff > best_eff * 1.0005) { best_eff = eff; best.splits = (int)splits; best.chunks_per_split = (int)cps; }
     }
     if (best_eff < 0) { best.splits = 1; best.chunks_per_split = (int)n_chunks; }
+    // developer override for A/B timing of the split count (tools/time_splits.py); never set in production
+    static const int forced = [] { const char* e = getenv("NB_B200_SPLITS"); return e ? atoi(e) : 0; }();
+    if (forced > 0 && forced <= max_splits && forced <= n_chunks) {
+        best.chunks_per_split = (int)((n_chunks + forced - 1) / forced);
+        best.splits = (int)((n_chunks + best.chunks_per_split - 1) / best.chunks_per_split);
+    }
     return best;
 }
 

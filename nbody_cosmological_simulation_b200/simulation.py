@@ -35,6 +35,7 @@ _INT_FORCE_SNAP = {PrecisionMode.INT8_SIM: 256, PrecisionMode.INT4_SIM: 16}     
 # writing through data_ptr) are invisible to them: call sim.invalidate_caches() after such a write, or set
 # NB_B200_NO_CACHE=1 to disable the caches altogether.
 _NO_CACHE = os.environ.get("NB_B200_NO_CACHE", "0") == "1"
+_PERSISTENT = os.environ.get("NB_B200_PERSISTENT", "1") != "0"                 # whole-span cooperative kernel for small systems
 _FUSE_PE = os.environ.get("NB_B200_FUSE_PE", "1") != "0" and not _NO_CACHE     # potential energy from the force pass
 
 
@@ -308,8 +309,10 @@ class GalaxySimulation:
             self.velocities = v
         self.tick += 1
 
-    # below this many particles a tick is launch-latency bound: replay it from a CUDA graph
+    # below this many particles a tick is launch-latency bound: replay it from a CUDA graph ...
     GRAPH_MAX_STARS = 65536
+    # ... and below this many, run whole spans of ticks as ONE persistent cooperative kernel (fp32 state, FLOAT32 mode)
+    PERSISTENT_MAX_STARS = 16384
 
     def _run_fused(self, ticks: int, spec=None):
         """`ticks` stock ticks in ONE native call (nb_run_ticks): the closing half kick of tick t is fused into the
@@ -343,7 +346,8 @@ class GalaxySimulation:
                                      code, L.dtype_code(m),
                                      L.MODE_CODES[mode.value], levels, snap_levels, float(self.G), float(self.softening_sq),
                                      float(min_dist_sq), float(self.dt), int(ticks), int(uni), m0, L.ptr(packed), L.ptr(table),
-                                     L.ptr(buf.scalars), L.ptr(ws), ws.numel(), int(n <= self.GRAPH_MAX_STARS),
+                                     L.ptr(buf.scalars), L.ptr(ws), ws.numel(),
+                                     (2 if (n <= self.PERSISTENT_MAX_STARS and _PERSISTENT) else 1) if n <= self.GRAPH_MAX_STARS else 0,
                                      L.ptr(pe_dev), L.stream_ptr(x.device)), "nb_run_ticks")
         self._packed_key = self._packed_cache_key(x, m, packed)      # packed holds the records of the final positions
         self.positions, self.velocities, self.accelerations = x, v, a

@@ -88,7 +88,7 @@ def test_bound_fraction_general_masses_fp64_and_3d():
     n = 30000
     pos, vel, mass = ora.uniform_box(n, seed=5, dim=3, dtype=torch.float64)
     mass = mass * (1.0 + (torch.arange(n) % 7).double()) * 3e3
-    vel = vel * 4.0
+    vel = vel * 150.0
     want = ora.bound_fraction(pos, vel, mass, 0.001)
     got = M.compute_bound_fraction(pos.to(DEV), vel.to(DEV), mass.to(DEV), 0.001)
     assert abs(got - want) <= 2.0 / n

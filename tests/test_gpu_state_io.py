@@ -42,9 +42,10 @@ def test_run_comparison_history_matches_oracle_history(mode):
     got = nb.run_comparison(pos.to(DEV), vel.to(DEV), mass.to(DEV), [nb.get_mode_from_string(mode)], num_ticks=ticks,
                             callback_interval=interval)[mode]["history"]
     assert got["ticks"] == want["ticks"] == [0, 20, 40, 60]
-    tol_e = 1e-12 if mode == "float64" else 3e-6
-    for a, b in zip(got["energies"], want["energies"]):
-        assert isinstance(a, float) and abs(a - b) <= tol_e * abs(b) + (0 if mode == "float64" else 0), (a, b)
+    for k, (a, b) in enumerate(zip(got["energies"], want["energies"])):
+        # FLOAT64 mode on fp32 inputs: the state (and with it the energy reductions) is fp32 at tick 0, fp64 afterwards
+        tol_e = 1e-12 if (mode == "float64" and k > 0) else 3e-6
+        assert isinstance(a, float) and abs(a - b) <= tol_e * abs(b), (k, a, b)
     for k, (a, b) in enumerate(zip(got["positions"], want["positions"])):
         assert a.device.type == "cpu" and not a.is_pinned() and a.dtype == b.dtype, k
         np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=0, atol=1e-12 if mode == "float64" and k else 2e-5)
