@@ -213,6 +213,8 @@ class GalaxySimulation:
         mode, levels, min_dist_sq, snap_levels = spec or self._force_spec() or \
             (self.precision_mode, levels_for_mode(self.precision_mode) or 0, 0.01, _INT_FORCE_SNAP.get(self.precision_mode, 0))
         mode_code = L.MODE_CODES[mode.value]
+        if levels and code == L.NB_F64:
+            return self._grid_force_on_fp64_state(x, m, mode, levels, min_dist_sq, snap_levels)
         out_dtype = torch.float64 if (code == L.NB_F64 or mode == PrecisionMode.FLOAT64) else torch.float32
         acc = torch.empty((n, dim), dtype=out_dtype, device=x.device)
         ws_bytes = max(lib.nb_accel_workspace_bytes(n, dim), lib.nb_max_dist_workspace_bytes(n) if levels else 0)
@@ -234,6 +236,34 @@ class GalaxySimulation:
                                  ws.numel(), st),
                     "nb_accel")
         return acc, snap_levels
+
+    def _grid_force_on_fp64_state(self, x, m, mode, levels, min_dist_sq, snap_levels):
+        """INT8_SIM / INT4_SIM / CUSTOM on an fp64 state (run_comparison(pos.double(), …, modes=[FLOAT64, INT4_SIM]), or a
+        FLOAT64-mode run whose promoted state is switched to an int mode).  The log-grid kernels are fp32: the pair loop
+        runs on an fp32 copy of the positions and the accelerations are widened; integrator, force snap and energies stay
+        fp64.  The d² quantiser keeps <= `levels` distinct values per pair, so the fp32 d² differs from the reference's
+        fp64 one only for pairs within ~1e-7 of a level boundary (the same class of flips as CPU-vs-CUDA logf ulps)."""
+        lib, buf = L.load(), self._buf()
+        x32, m32 = x.float().contiguous(), m.float().contiguous()
+        n, dim = x32.shape
+        packed = buf.bytes("packed_f32_aux", lib.nb_packed_bytes(n, dim, L.NB_F32))
+        acc = torch.empty((n, dim), dtype=torch.float32, device=x.device)
+        ws = buf.bytes("accel_ws", max(lib.nb_accel_workspace_bytes(n, dim), lib.nb_max_dist_workspace_bytes(n)))
+        table = buf.bytes("level_table", lib.nb_level_table_bytes(levels))
+        eps_sq = float(self.softening_sq)
+        uni, m0 = L.uniform_mass(m32)
+        with L.on_device(x.device):
+            st = L.stream_ptr(x.device)
+            L.check(lib.nb_pack_sources(L.ptr(x32), L.ptr(m32), n, dim, L.NB_F32, L.NB_F32, L.ptr(packed), 0, st), "nb_pack_sources")
+            L.check(lib.nb_reset_scalars(L.ptr(buf.scalars), st), "nb_reset_scalars")
+            L.check(lib.nb_max_dist_sq(L.ptr(packed), n, dim, L.NB_F32, eps_sq, L.ptr(buf.scalars), L.ptr(ws), ws.numel(), st),
+                    "nb_max_dist_sq")
+            L.check(lib.nb_build_level_table(L.ptr(buf.scalars), L.NB_F32, eps_sq, float(min_dist_sq), float(self.G), levels,
+                                             L.ptr(table), st), "nb_build_level_table")
+            L.check(lib.nb_accel(L.ptr(packed), n, L.ptr(x32), n, dim, L.NB_F32, L.MODE_CODES[mode.value], float(self.G), eps_sq,
+                                 L.ptr(table), levels, int(uni), m0, L.ptr(acc), L.ptr(buf.scalars), L.ptr(ws), ws.numel(), st),
+                    "nb_accel")
+        return acc.double(), snap_levels
 
     def _compute_accelerations(self) -> torch.Tensor:
         """Gravitational accelerations of all stars in the current precision mode (overridable hook)."""
@@ -283,7 +313,7 @@ class GalaxySimulation:
         """One kick-drift-kick leapfrog tick (reference simulation.py:120-143)."""
         spec = self._force_spec()                  # None: the force hook is user code
         stock_force = spec is not None
-        if stock_force and not getattr(self, "_explicit_step", False):
+        if stock_force and not getattr(self, "_explicit_step", False) and self._fusable(spec):
             # one native call (kick-drift, force, closing kick) instead of four calls from Python; bit-identical to the
             # explicit sequence below, which stays for instrumentation (bench.py times the force launch with it)
             self._run_fused(1, spec)
@@ -308,6 +338,14 @@ class GalaxySimulation:
                 self.positions = x
             self.velocities = v
         self.tick += 1
+
+    def _fusable(self, spec) -> bool:
+        """nb_run_ticks covers every combination except a log-grid mode on an fp64 state (evaluated on an fp32 copy, see
+        _grid_force_on_fp64_state), which takes the call-by-call path."""
+        if not spec[1]:
+            return True
+        dt = torch.promote_types(torch.promote_types(self.positions.dtype, self.velocities.dtype), self.accelerations.dtype)
+        return dt != torch.float64
 
     # below this many particles a tick is launch-latency bound: replay it from a CUDA graph ...
     GRAPH_MAX_STARS = 65536
@@ -371,7 +409,7 @@ class GalaxySimulation:
             # re-read every span: a callback may switch precision_mode, a recognised override's level count, the
             # state dtype, or patch step()/_compute_accelerations on the instance (the reference re-reads per tick)
             spec = self._force_spec() if self._is_stock(self, "step") else None
-            if spec is None:
+            if spec is None or not self._fusable(spec):
                 self.step()
                 done += 1
             else:

@@ -227,3 +227,33 @@ def test_caches_survive_recycled_tensor_addresses():
         assert_forces_close(got.cpu(), ref.acc, pos * scale, m * scale, 0.001, 0.1, 1e-5, 2.0 ** -24)
         if sim.positions.data_ptr() == old_x and sim.masses.data_ptr() == old_m:
             break
+
+
+def test_int_modes_on_an_fp64_state():
+    """run_comparison(pos.double(), …, modes=[FLOAT64, INT4_SIM]) and a promoted FLOAT64 run switched to an int
+    mode must work.  The log-grid pair loop runs on an fp32 copy (documented in simulation._grid_force_on_fp64_state):
+    against the oracle's all-fp64 evaluation only pairs on a level boundary may differ."""
+    import nbody_cosmological_simulation_b200 as nb
+    torch.manual_seed(12)
+    pos, vel, mass = nb.create_disk_galaxy(1200, device=torch.device("cpu"))
+    pos, vel, mass = pos.double(), vel.double(), mass.double()
+    for mode in ("int4_sim", "int8_sim", "custom"):
+        sim = nb.GalaxySimulation(pos.to(DEV), vel.to(DEV), mass.to(DEV), precision_mode=nb.get_mode_from_string(mode))
+        ref = ora.State(pos, vel, mass, mode=mode)
+        assert sim.accelerations.dtype == torch.float64
+        a, b = sim.accelerations.cpu().numpy(), ref.acc.numpy()
+        same = np.abs(a - b) <= 1e-5 * np.abs(b).max()
+        assert same.mean() >= 0.99, (mode, same.mean())
+        sim.run(5)
+        ref.run(5)
+        assert sim.positions.dtype == torch.float64 and sim.tick == 5
+        assert float((sim.positions.cpu() - ref.pos).abs().max()) <= 1e-4
+        assert abs(sim.get_total_energy() - ref.total()) <= 2e-3 * abs(ref.total())
+    res = nb.run_comparison(pos.to(DEV), vel.to(DEV), mass.to(DEV), [nb.PrecisionMode.FLOAT64, nb.PrecisionMode.INT4_SIM],
+                            num_ticks=10, callback_interval=5)
+    assert set(res) == {"float64", "int4_sim"} and res["int4_sim"]["final_state"]["positions"].dtype == torch.float64
+    sw = nb.GalaxySimulation(pos.float().to(DEV), vel.float().to(DEV), mass.float().to(DEV), precision_mode=nb.PrecisionMode.FLOAT64)
+    sw.run(3)                                             # the state is fp64 now
+    sw.precision_mode = nb.PrecisionMode.INT8_SIM
+    sw.run(3)
+    assert sw.tick == 6 and bool(torch.isfinite(sw.positions).all())
