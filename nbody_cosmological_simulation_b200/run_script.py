@@ -16,7 +16,27 @@ DROPIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin")
 REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _join_process_group():
+    """Under torchrun (RANK / WORLD_SIZE set, more than one rank): one rank per GPU over NCCL.  `GalaxySimulation` then
+    splits its O(N²) work across the ranks by itself (simulation._ReplicatedShards); the script stays unchanged.  Ranks
+    other than 0 run silently so that the script's prints appear once."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1 or os.environ.get("NB_B200_DISTRIBUTED", "1") == "0":
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available() or dist.is_initialized():
+        return
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if dist.get_rank() != 0:
+        sys.stdout = open(os.devnull, "w")
+
+
 def run(script: str, argv=None):
+    _join_process_group()
     for p in (REPO_ROOT, DROPIN_DIR):
         if p in sys.path:
             sys.path.remove(p)

@@ -55,6 +55,58 @@ class _DeviceBuffers:
         return buf
 
 
+class _ReplicatedShards:
+    """Multi-GPU mode of `GalaxySimulation` itself, for scripts written against the reference (which knows nothing about
+    ranks): launched under torchrun with NCCL, every rank runs the SAME script and holds the FULL state; only the O(N²)
+    work is split — rank r evaluates the force (and its share of the potential) for the targets of its chunk-aligned
+    i-range against all sources and the ranks all-gather the accelerations (N·D·w bytes per tick).  The O(N) integrator
+    runs redundantly and deterministically on every rank, so the replicas stay bit-identical.  The initial state is
+    broadcast from rank 0 (the reference's scripts do not seed their RNG: every rank would draw a different galaxy).
+    Chosen automatically when torch.distributed is initialised with more than one rank; NB_B200_DISTRIBUTED=0 turns it
+    off.  `sharded.ShardedGalaxySimulation` is the engine that also shards the STATE (and hides the gather)."""
+
+    def __init__(self, n: int, state_dtype, device):
+        import torch.distributed as dist
+        from .sharded import ShardPlan
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        chunk = int(L.load().nb_chunk_sources(L.NB_F32 if state_dtype == torch.float32 else L.NB_F64))
+        # a plan in fp32 chunks (256) stays chunk-aligned after the fp32 -> fp64 promotion (128)
+        chunk = max(chunk, 256)
+        world = min(self.world, max(1, -(-n // chunk)))
+        self.plan = ShardPlan(n, world, chunk)
+        self.active = self.rank < world                    # tiny systems: the surplus ranks contribute nothing
+        self.i0 = self.plan.start[self.rank] if self.active else 0
+        self.count = self.plan.count[self.rank] if self.active else 0
+        self.rows = max(self.plan.count)
+        self.device = device
+
+    @staticmethod
+    def wanted(device) -> bool:
+        try:
+            import torch.distributed as dist
+        except ImportError:
+            return False
+        return (os.environ.get("NB_B200_DISTRIBUTED", "1") != "0" and dist.is_available() and dist.is_initialized()
+                and dist.get_world_size() > 1 and torch.device(device).type == "cuda")
+
+    def broadcast(self, *tensors):
+        for t in tensors:
+            self.dist.broadcast(t, src=0)
+
+    def gather_rows(self, local: torch.Tensor, n: int) -> torch.Tensor:
+        """(n, D) from the per-rank row slices (padded to equal size for the collective)."""
+        pad = torch.zeros((self.rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+        out = torch.empty((self.world * self.rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        self.dist.all_gather_into_tensor(out, pad)
+        parts = [out[r * self.rows: r * self.rows + self.plan.count[r]] for r in range(self.plan.world)]
+        return torch.cat(parts, dim=0)
+
+    def all_reduce(self, t, op):
+        self.dist.all_reduce(t, op=op)
+
+
 class _DeferredPE:
     """Σ_{i<j} m_i m_j / r_ij left in device memory by a potential-carrying force pass (nb_run_ticks pe_out)."""
     __slots__ = ("dev", "G", "dtype")
@@ -94,6 +146,10 @@ class GalaxySimulation:
 
         self._buffers: Optional[_DeviceBuffers] = None
         self._packed_key = None
+        self._shards = None
+        if _ReplicatedShards.wanted(self.device):
+            self._shards = _ReplicatedShards(self.num_stars, self.positions.dtype, self.device)
+            self._shards.broadcast(self.positions, self.velocities, self.masses)
 
         # reference simulation.py:69 — one force evaluation at construction (through the hook; a recognised
         # script override is evaluated natively, see _force_spec)
@@ -231,10 +287,25 @@ class GalaxySimulation:
                 table = buf.bytes("level_table", lib.nb_level_table_bytes(levels))
                 L.check(lib.nb_build_level_table(L.ptr(buf.scalars), code, eps_sq, min_dist_sq, float(self.G), levels,
                                                  L.ptr(table), st), "nb_build_level_table")
-            L.check(lib.nb_accel(L.ptr(packed), n, L.ptr(x), n, dim, code, mode_code, float(self.G), eps_sq,
-                                 L.ptr(table), levels, int(uni), m0, L.ptr(acc), L.ptr(buf.scalars), L.ptr(ws),
-                                 ws.numel(), st),
-                    "nb_accel")
+            sh = getattr(self, "_shards", None)
+            if sh is None:
+                L.check(lib.nb_accel(L.ptr(packed), n, L.ptr(x), n, dim, code, mode_code, float(self.G), eps_sq,
+                                     L.ptr(table), levels, int(uni), m0, L.ptr(acc), L.ptr(buf.scalars), L.ptr(ws),
+                                     ws.numel(), st),
+                        "nb_accel")
+            else:
+                # replicated state, sharded pair work: this rank's i-range against all sources, accelerations all-gathered
+                xs = x[sh.i0: sh.i0 + sh.count]
+                part = torch.empty((sh.count, dim), dtype=out_dtype, device=x.device)
+                if sh.count:
+                    L.check(lib.nb_accel(L.ptr(packed), n, L.ptr(xs), sh.count, dim, code, mode_code, float(self.G), eps_sq,
+                                         L.ptr(table), levels, int(uni), m0, L.ptr(part), L.ptr(buf.scalars), L.ptr(ws),
+                                         ws.numel(), st),
+                            "nb_accel")
+                acc = sh.gather_rows(part, n)
+                if snap_levels:                # INT8/INT4: the snap grid spans the extrema over ALL ranks' accelerations
+                    sh.all_reduce(buf.scalars[L.SLOT_ACC_MIN:L.SLOT_ACC_MIN + 1], sh.dist.ReduceOp.MIN)
+                    sh.all_reduce(buf.scalars[L.SLOT_ACC_MAX:L.SLOT_ACC_MAX + 1], sh.dist.ReduceOp.MAX)
         return acc, snap_levels
 
     def _grid_force_on_fp64_state(self, x, m, mode, levels, min_dist_sq, snap_levels):
@@ -342,6 +413,8 @@ class GalaxySimulation:
     def _fusable(self, spec) -> bool:
         """nb_run_ticks covers every combination except a log-grid mode on an fp64 state (evaluated on an fp32 copy, see
         _grid_force_on_fp64_state), which takes the call-by-call path."""
+        if getattr(self, "_shards", None) is not None:
+            return False                       # replicated multi-GPU mode: the force is a sliced launch + all-gather per tick
         if not spec[1]:
             return True
         dt = torch.promote_types(torch.promote_types(self.positions.dtype, self.velocities.dtype), self.accelerations.dtype)
@@ -490,10 +563,21 @@ class GalaxySimulation:
         packed = self._pack(x, m)
         out = torch.empty(1, dtype=torch.float64, device=x.device)
         ws = buf.bytes("energy_ws", lib.nb_energy_workspace_bytes(n))
+        sh = getattr(self, "_shards", None)
         with L.on_device(x.device):
-            L.check(lib.nb_potential_energy(L.ptr(packed), n, L.ptr(x), L.ptr(m), n, 0, dim, L.dtype_code(x),
-                                            L.dtype_code(m), float(self.softening_sq), L.ptr(out), L.ptr(ws),
-                                            ws.numel(), L.stream_ptr(x.device)), "nb_potential_energy")
+            if sh is None:
+                L.check(lib.nb_potential_energy(L.ptr(packed), n, L.ptr(x), L.ptr(m), n, 0, dim, L.dtype_code(x),
+                                                L.dtype_code(m), float(self.softening_sq), L.ptr(out), L.ptr(ws),
+                                                ws.numel(), L.stream_ptr(x.device)), "nb_potential_energy")
+            else:
+                # this rank's targets take their half ring of source chunks (equal work on every rank); ranks add up
+                out.zero_()
+                if sh.count:
+                    xs, ms = x[sh.i0: sh.i0 + sh.count], m[sh.i0: sh.i0 + sh.count]
+                    L.check(lib.nb_potential_energy(L.ptr(packed), n, L.ptr(xs), L.ptr(ms), sh.count, sh.i0, dim,
+                                                    L.dtype_code(x), L.dtype_code(m), float(self.softening_sq), L.ptr(out),
+                                                    L.ptr(ws), ws.numel(), L.stream_ptr(x.device)), "nb_potential_energy")
+                sh.all_reduce(out, sh.dist.ReduceOp.SUM)
         return out, torch.promote_types(x.dtype, m.dtype)
 
     def _total_energy_deferred(self):

@@ -46,7 +46,11 @@ def test_c2_sized_sweep_runs_unchanged(tmp_path):
         assert abs(e[0] - e64[0]) <= 3e-6 * abs(e64[0])                  # same initial state in every mode
         drift = abs(e[-1] - e[0]) / abs(e[0])
         # leapfrog at dt = 0.01 itself drifts ~1.2e-4 here (float64: 1.23e-4 measured); the float modes must sit on that curve
-        assert drift < (0.05 if mode == "int4_sim" else 2e-3 if mode == "int8_sim" else 3e-4), (mode, drift)
+        # int4 at this N: the unmodified reference on CPU (seed 0) drifts +6.0 % / +9.1 % / +11.2 % at ticks 50 / 100 / 150
+        # (16 force levels over 10^4 stars); the CUDA path measured 17.9 % at tick 200 on the box's own random galaxy
+        assert drift < (0.30 if mode == "int4_sim" else 2e-3 if mode == "int8_sim" else 3e-4), (mode, drift)
+        if mode == "int4_sim":
+            assert drift > 0.03                                  # ... and it must not be suspiciously quiet either
         if mode in ("float32", "float16"):
             assert abs(e[-1] - e64[-1]) <= 2e-5 * abs(e64[-1]), (mode, e[-1], e64[-1])
     assert s["override_vs_custom_rel"] < 1e-5
