@@ -155,7 +155,7 @@ int nb_accel_potential(const void* packed_src, int64_t n_src, const void* pos_tg
                        double mass_value, void* acc_out, double* pe_out, void* workspace, int64_t workspace_bytes,
                        void* stream);
 
-/* Windowed force evaluation for i-range-sharded ticks (float modes only).  nb_accel_window streams the source chunks
+/* Windowed force evaluation for i-range-sharded ticks (fp32 state in FLOAT32 mode, fp64 state in FLOAT64 mode).  nb_accel_window streams the source chunks
  * [first_chunk, first_chunk + n_chunks) of the packed set — taken modulo ring_chunks when ring_chunks > 0, so a window may
  * wrap past the last chunk — and APPENDS its j-split partial sums to `workspace` behind the `splits_before` split slots
  * earlier windows of the same evaluation wrote; *splits_total_out = splits_before + the slots it added (max_splits > 0 caps

@@ -34,6 +34,12 @@ namespace nb {
 #ifndef NB_LUTF_THREADS
 #define NB_LUTF_THREADS 256
 #endif
+#ifndef NB_F32_PERTURB
+#define NB_F32_PERTURB 0              // source-order perturbations of the float pair loop (same arithmetic up to the d² summation order)
+#endif
+#ifndef NB_F32_ACC_VARIANT
+#define NB_F32_ACC_VARIANT 0          // how the float kernels write the three accumulates (tools/f32_loop_probe.sh compares)
+#endif
 enum QMode { Q_F32 = 0, Q_F16 = 1, Q_BF16 = 2, Q_LUT = 3, Q_F64 = 4, Q_LUTF = 5 };   // Q_LUTF: fast level lookup (lut.cuh), L <= 256
 
 struct AccelArgs {
@@ -54,10 +60,7 @@ struct AccelArgs {
     float uniform_mass;       // Q_LUTF: != 0 when every real source has this mass (the per-pair mass multiply is dropped)
     int splits_before;        // windowed evaluation: split slots already used by earlier windows
     int max_splits;           // > 0: cap on the split count of this launch
-    int tile, split;          // persistent whole-tick kernel: this CTA's task (target tile, source split) + 1; 0 = blockIdx.x / .y
 };
-__device__ __forceinline__ int tile_of(const AccelArgs& a) { return a.tile ? a.tile - 1 : (int)blockIdx.x; }
-__device__ __forceinline__ int split_of(const AccelArgs& a) { return a.split ? a.split - 1 : (int)blockIdx.y; }
 
 // Level table layout (Q_LUT): float4 entry[k] = { T_{k+1}, g_k, g_{k+1}, 0 } for k = 0..L-1, preceded by a
 // 16-byte header { lo2 (log2 of lower bound), scale (levels-1)/(hi2-lo2), min_val, degenerate flag }
@@ -100,11 +103,11 @@ struct ForceF32 {
     bool clamp_lo;                         // eps² < min_val: d² must be clamped from below (quantization.py:106)
     float inv_uniform_mass;                // 1/m when all real sources have mass m (0: general masses)
 
-    __device__ __forceinline__ void init(const AccelArgs& a, const float4* lut_smem) {
+    __device__ __forceinline__ void init(const AccelArgs& a, const float4* lut_smem, int tile) {
         const float* pos = reinterpret_cast<const float*>(a.pos_tgt);
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
-            int64_t i = (int64_t)tile_of(a) * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            int64_t i = (int64_t)tile * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i >= a.n_tgt) i = a.n_tgt - 1;
             const float x = pos[i * DIM + 0], y = pos[i * DIM + 1], z = DIM == 3 ? pos[i * DIM + 2] : 0.f;
             nx[t] = make_float2(-x, -x); ny[t] = make_float2(-y, -y); nz[t] = make_float2(-z, -z);
@@ -199,10 +202,17 @@ struct ForceF32 {
     template <bool FUSED = (QMODE == Q_F32)>
     __device__ __forceinline__ float2 dist_sq(float2 dx, float2 dy, float2 dz) const {
         if (FUSED) {
+#if NB_F32_PERTURB & 2
+            float2 d2 = DIM == 3 ? fma2(dz, dz, eps2) : eps2;
+            d2 = fma2(dy, dy, d2);
+            d2 = fma2(dx, dx, d2);
+            return d2;
+#else
             float2 d2 = fma2(dx, dx, eps2);
             d2 = fma2(dy, dy, d2);
             if (DIM == 3) d2 = fma2(dz, dz, d2);
             return d2;
+#endif
         } else {
             // The reference's exact rounding sequence rn(rn(rn(dx²)+rn(dy²))[+rn(dz²)])+ε²) with packed ops.  ptxas
             // contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (seen in SASS; changes d² by an ulp and flips fp16/bf16/
@@ -355,9 +365,15 @@ struct ForceF32 {
             if (DIM == 3) { const float4 b = B4[p]; zs = make_float2(b.x, b.y); ms = make_float2(b.z, b.w); }
             else ms = B2[p];
 #pragma unroll
-            for (int t = 0; t < IPT; ++t) {
+            for (int tt = 0; tt < IPT; ++tt) {
+                const int t = (NB_F32_PERTURB & 4) ? IPT - 1 - tt : tt;
+#if NB_F32_PERTURB & 1
+                const float2 dy = add2(ys, ny[t]);
+                const float2 dx = add2(xs, nx[t]);              // diff = pos[j] − pos[i]   simulation.py:83
+#else
                 const float2 dx = add2(xs, nx[t]);              // diff = pos[j] − pos[i]   simulation.py:83
                 const float2 dy = add2(ys, ny[t]);
+#endif
                 float2 dz = make_float2(0.f, 0.f);
                 if (DIM == 3) dz = add2(zs, nz[t]);
                 float2 d2 = dist_sq(dx, dy, dz);
@@ -373,7 +389,7 @@ struct ForceF32 {
                         d2 = __bfloat1622float2(h);
                     }
                     const float2 r = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
-                    if (ULOOP) w = mul2(mul2(r, r), r);         // 1 / d²^1.5 (common mass applied at the flush / in finalize)
+                    if (ULOOP) w = (NB_F32_PERTURB & 8) ? mul2(r, mul2(r, r)) : mul2(mul2(r, r), r);   // 1 / d²^1.5 (common mass applied at the flush / in finalize)
                     else w = mul2(mul2(r, r), mul2(r, ms));     // m_j / d²^1.5             simulation.py:97-105
                     if (PHI) ap[t] = ULOOP ? add2(r, ap[t]) : fma2(ms, r, ap[t]);    // Σ_j m_j / r_ij   simulation.py:185-188
                 }
@@ -381,23 +397,45 @@ struct ForceF32 {
                 // register pairs issues in 3 cycles, not 2 (two banks, one 64-lane read each per cycle), so this loop's
                 // floor is 6+6+4+9 = 25 cycles per 64 interactions, not 22.  Tried and measured slower: scalar FFMAs on
                 // the halves (x-halves are all even registers: 2-3 cycles each) and a 3-instruction asm block.
+#if NB_F32_ACC_VARIANT == 1
+                // the three accumulates as ONE asm statement: ptxas keeps them adjacent, so `w` stays in the operand-reuse
+                // cache for the second and third (an FFMA2 with three distinct register pairs costs 3 issue cycles, one with
+                // a reused operand 2)
+                if (DIM == 3) {
+                    asm("{\n\t.reg .b64 w, a, b, c, x, y, z;\n\t"
+                        "mov.b64 w, {%6, %7};\n\tmov.b64 a, {%8, %9};\n\tmov.b64 b, {%10, %11};\n\tmov.b64 c, {%12, %13};\n\t"
+                        "mov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\tmov.b64 z, {%4, %5};\n\t"
+                        "fma.rn.f32x2 x, w, a, x;\n\tfma.rn.f32x2 y, w, b, y;\n\tfma.rn.f32x2 z, w, c, z;\n\t"
+                        "mov.b64 {%0, %1}, x;\n\tmov.b64 {%2, %3}, y;\n\tmov.b64 {%4, %5}, z;\n\t}"
+                        : "+f"(ax[t].x), "+f"(ax[t].y), "+f"(ay[t].x), "+f"(ay[t].y), "+f"(az[t].x), "+f"(az[t].y)
+                        : "f"(w.x), "f"(w.y), "f"(dx.x), "f"(dx.y), "f"(dy.x), "f"(dy.y), "f"(dz.x), "f"(dz.y));
+                } else {
+                    ax[t] = fma2(w, dx, ax[t]);
+                    ay[t] = fma2(w, dy, ay[t]);
+                }
+#elif NB_F32_ACC_VARIANT == 3
+                if (DIM == 3) az[t] = fma2(w, dz, az[t]);
+                ay[t] = fma2(w, dy, ay[t]);
+                ax[t] = fma2(w, dx, ax[t]);
+#else
                 ax[t] = fma2(w, dx, ax[t]);
                 ay[t] = fma2(w, dy, ay[t]);
                 if (DIM == 3) az[t] = fma2(w, dz, az[t]);
+#endif
             }
         }
         flush(chunk_mass);
     }
 
-    __device__ __forceinline__ void store(const AccelArgs& a) const {
-        double* out = a.partial + (int64_t)split_of(a) * a.n_tgt * DIM;
+    __device__ __forceinline__ void store(const AccelArgs& a, int tile, int split) const {
+        double* out = a.partial + (int64_t)split * a.n_tgt * DIM;
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
-            const int64_t i = (int64_t)tile_of(a) * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            const int64_t i = (int64_t)tile * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i < a.n_tgt) {
                 out[i * DIM + 0] = sx[t]; out[i * DIM + 1] = sy[t];
                 if (DIM == 3) out[i * DIM + 2] = sz[t];
-                if (PHI) a.partial_phi[(int64_t)split_of(a) * a.n_tgt + i] = sp[t];
+                if (PHI) a.partial_phi[(int64_t)split * a.n_tgt + i] = sp[t];
             }
         }
     }
@@ -441,11 +479,11 @@ struct ForceF64 {
     double sp[IPT];
     double eps2;
 
-    __device__ __forceinline__ void init(const AccelArgs& a, const float4*) {
+    __device__ __forceinline__ void init(const AccelArgs& a, const float4*, int tile) {
         const double* pos = reinterpret_cast<const double*>(a.pos_tgt);
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
-            int64_t i = (int64_t)tile_of(a) * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            int64_t i = (int64_t)tile * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i >= a.n_tgt) i = a.n_tgt - 1;
             xi[t] = pos[i * DIM + 0]; yi[t] = pos[i * DIM + 1]; zi[t] = DIM == 3 ? pos[i * DIM + 2] : 0.0;
             sx[t] = sy[t] = sz[t] = 0.0;
@@ -520,15 +558,15 @@ struct ForceF64 {
             }
         }
     }
-    __device__ __forceinline__ void store(const AccelArgs& a) const {
-        double* out = a.partial + (int64_t)split_of(a) * a.n_tgt * DIM;
+    __device__ __forceinline__ void store(const AccelArgs& a, int tile, int split) const {
+        double* out = a.partial + (int64_t)split * a.n_tgt * DIM;
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
-            const int64_t i = (int64_t)tile_of(a) * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            const int64_t i = (int64_t)tile * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i < a.n_tgt) {
                 out[i * DIM + 0] = sx[t]; out[i * DIM + 1] = sy[t];
                 if (DIM == 3) out[i * DIM + 2] = sz[t];
-                if (PHI) a.partial_phi[(int64_t)split_of(a) * a.n_tgt + i] = sp[t];
+                if (PHI) a.partial_phi[(int64_t)split * a.n_tgt + i] = sp[t];
             }
         }
     }
@@ -544,11 +582,11 @@ struct ForceMixed {       // fp32 sources/targets, FLOAT64 mode
     double sx[IPT], sy[IPT], sz[IPT];
     float eps2;
 
-    __device__ __forceinline__ void init(const AccelArgs& a, const float4*) {
+    __device__ __forceinline__ void init(const AccelArgs& a, const float4*, int tile) {
         const float* pos = reinterpret_cast<const float*>(a.pos_tgt);
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
-            int64_t i = (int64_t)tile_of(a) * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            int64_t i = (int64_t)tile * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i >= a.n_tgt) i = a.n_tgt - 1;
             xi[t] = pos[i * DIM + 0]; yi[t] = pos[i * DIM + 1]; zi[t] = DIM == 3 ? pos[i * DIM + 2] : 0.f;
             sx[t] = sy[t] = sz[t] = 0.0;
@@ -583,11 +621,11 @@ struct ForceMixed {       // fp32 sources/targets, FLOAT64 mode
             }
         }
     }
-    __device__ __forceinline__ void store(const AccelArgs& a) const {
-        double* out = a.partial + (int64_t)split_of(a) * a.n_tgt * DIM;
+    __device__ __forceinline__ void store(const AccelArgs& a, int tile, int split) const {
+        double* out = a.partial + (int64_t)split * a.n_tgt * DIM;
 #pragma unroll
         for (int t = 0; t < IPT; ++t) {
-            const int64_t i = (int64_t)tile_of(a) * (THREADS * IPT) + t * THREADS + threadIdx.x;
+            const int64_t i = (int64_t)tile * (THREADS * IPT) + t * THREADS + threadIdx.x;
             if (i < a.n_tgt) {
                 out[i * DIM + 0] = sx[t]; out[i * DIM + 1] = sy[t];
                 if (DIM == 3) out[i * DIM + 2] = sz[t];
@@ -602,7 +640,10 @@ struct ForceMixed {       // fp32 sources/targets, FLOAT64 mode
 constexpr int kMaxLevelsSmem = 4096;      // level table entries staged in shared memory (64 KB + header)
 
 // LUTKIND: 0 = no level table, 1 = 16-byte entries replicated per bank group (Q_LUT), 2 = fast lookup (Q_LUTF)
-template <class Consumer, int LUTKIND>
+// WINDOW: the launch streams a window [chunk0, chunk0 + n_chunks) of the packed set, modulo `ring` (sharded ticks);
+// a template parameter so that the ordinary kernels keep exactly the code (and the ptxas schedule) they are tuned with —
+// the packed-FMA loop is register-bank limited and a different register assignment costs several per cent.
+template <class Consumer, int LUTKIND, bool WINDOW = false>
 __global__ void __launch_bounds__(Consumer::THREADS + 32, LUTKIND == 2 ? NB_LUTF_MINB : (Consumer::HAS_PHI ? 3 : 0)) accel_kernel(const AccelArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const bool is_consumer = threadIdx.x < Consumer::THREADS;
@@ -631,12 +672,13 @@ __global__ void __launch_bounds__(Consumer::THREADS + 32, LUTKIND == 2 ? NB_LUTF
         __syncthreads();
     }
     Consumer cons;
-    if (is_consumer) cons.init(a, lut_smem);
+    if (is_consumer) cons.init(a, lut_smem, blockIdx.x);
     if constexpr (LUTKIND == 1) cons.levels_m1_f = (float)(a.levels - 1);
     const int64_t c0 = (int64_t)blockIdx.y * a.chunks_per_split;
     const int64_t c1 = min(a.n_chunks, c0 + (int64_t)a.chunks_per_split);
-    stream_sources(a.src, a.chunk0 + c0, a.chunk0 + c1, cons, a.ring);
-    if (is_consumer) cons.store(a);
+    if constexpr (WINDOW) stream_sources(a.src, a.chunk0 + c0, a.chunk0 + c1, cons, a.ring);
+    else stream_sources(a.src, c0, c1, cons);
+    if (is_consumer) cons.store(a, blockIdx.x, blockIdx.y);
 }
 
 // acc_out[i,k] = scale · Σ_splits partial;  optional min/max of the outputs -> scalars (quantization.py:78-79)
@@ -767,9 +809,8 @@ __global__ void __launch_bounds__(Consumer::THREADS + 32, 2) persistent_ticks_ke
     cg::grid_group grid = cg::this_grid();
     const bool is_consumer = threadIdx.x < Consumer::THREADS;
     const int tasks = p.tiles * p.splits;
-    AccelArgs a = p.a;
-    a.tile = (int)(blockIdx.x % p.tiles) + 1;
-    a.split = (int)(blockIdx.x / p.tiles) + 1;
+    const AccelArgs& a = p.a;
+    const int tile = (int)(blockIdx.x % p.tiles), split = (int)(blockIdx.x / p.tiles);
     const double* partial = p.partial_in;
     int splits = p.splits_in;
     for (int t = 0; t < p.ticks; ++t) {
@@ -780,11 +821,11 @@ __global__ void __launch_bounds__(Consumer::THREADS + 32, 2) persistent_ticks_ke
         asm volatile("fence.proxy.async;" ::: "memory");
         if ((int)blockIdx.x < tasks) {
             Consumer cons;
-            if (is_consumer) cons.init(a, nullptr);
-            const int64_t c0 = (int64_t)(a.split - 1) * a.chunks_per_split;
+            if (is_consumer) cons.init(a, nullptr, tile);
+            const int64_t c0 = (int64_t)split * a.chunks_per_split;
             const int64_t c1 = min(a.n_chunks, c0 + (int64_t)a.chunks_per_split);
             stream_sources(a.src, c0, c1, cons);
-            if (is_consumer) cons.store(a);
+            if (is_consumer) cons.store(a, tile, split);
         }
         __threadfence();
         grid.sync();
@@ -805,7 +846,7 @@ constexpr int64_t kPhiBlockBytes = 16 * 1024;        // per-CTA partial sums of 
 struct ForceProfile { void* start; void* stop; int launches; };       // stop is recorded after the `launches`-th launch
 inline ForceProfile& force_profile() { static thread_local ForceProfile p{nullptr, nullptr, 0}; return p; }
 
-template <class Consumer, int LUTKIND>
+template <class Consumer, int LUTKIND, bool WINDOW = false>
 int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, int* splits_out, double** phi_out = nullptr) {
     AccelArgs a = a0;
     // a windowed launch appends its split slots behind the ones earlier windows of the same evaluation wrote
@@ -828,7 +869,7 @@ int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, 
         const int P = lut_pow2ceil(a.levels);
         smem += P * 128 + (P + 1 + 3) / 4 * 16;
     }
-    auto kern = accel_kernel<Consumer, LUTKIND>;
+    auto kern = accel_kernel<Consumer, LUTKIND, WINDOW>;
     int ctas_per_sm = 1;
     const int frc = kernel_occupancy((const void*)kern, Consumer::THREADS + 32, smem, &ctas_per_sm);
     if (frc != NB_OK) return frc;
@@ -876,6 +917,13 @@ int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, 
     AccelArgs a{};
     a.src = (const char*)packed_src;
     a.n_chunks = nb_num_chunks(n_src, dtype);
+    // developer A/B switch (tools/time_splits.py): run ordinary launches through the WINDOW instantiation, whose ptxas schedule
+    // differs (operand-reuse flags in the packed-FMA loop), over the whole source set
+    static const bool force_window_kernel = [] { const char* e = getenv("NB_B200_WINDOW_KERNEL"); return e && atoi(e) != 0; }();
+    SourceWindow whole{0, a.n_chunks, 0, 0, 0};
+    if (!window && force_window_kernel && !lut && !want_phi &&
+        ((dtype == NB_F32 && mode == NB_MODE_FLOAT32) || (dtype == NB_F64 && mode == NB_MODE_FLOAT64)))
+        window = &whole;
     if (window) {
         // a window of the packed set [first, first + count), modulo ring_chunks when the window wraps (float modes only)
         if (lut || want_phi || window->first_chunk < 0 || window->n_chunks <= 0 || window->splits_before < 0) return NB_ERR_INVALID_ARGUMENT;
@@ -906,6 +954,18 @@ int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, 
 #define NB_F32_UNI_CASE(D, Q) rc = launch_accel<ForceF32<D, Q, IPT, TH, true>, 0>(a, workspace_bytes, st, &splits)
 #define NB_F32_CASE(D, Q, LUT) rc = launch_accel<ForceF32<D, Q, IPT, TH>, LUT>(a, workspace_bytes, st, &splits)
 #define NB_F64_CASE(D, Q) rc = launch_accel<ForceF64<D, Q, IPT, TH>, 0>(a, workspace_bytes, st, &splits)
+#define NB_WIN_CASE(F, D, Q, U, UNR) rc = launch_accel<F<D, Q, IPT, TH, U, UNR>, 0, true>(a, workspace_bytes, st, &splits)
+    if (window) {
+        // windowed launches exist where the pair loop sees the state dtype's own d²: fp32 / FLOAT32 and fp64 / FLOAT64
+        if (dtype == NB_F32 && mode == NB_MODE_FLOAT32) {
+            if (uni) { if (dim == 2) NB_WIN_CASE(ForceF32, 2, Q_F32, true, 4); else NB_WIN_CASE(ForceF32, 3, Q_F32, true, 4); }
+            else { if (dim == 2) NB_WIN_CASE(ForceF32, 2, Q_F32, false, 4); else NB_WIN_CASE(ForceF32, 3, Q_F32, false, 4); }
+        } else if (dtype == NB_F64 && mode == NB_MODE_FLOAT64) {
+            if (uni) { if (dim == 2) NB_WIN_CASE(ForceF64, 2, Q_F64, true, 2); else NB_WIN_CASE(ForceF64, 3, Q_F64, true, 2); }
+            else { if (dim == 2) NB_WIN_CASE(ForceF64, 2, Q_F64, false, 2); else NB_WIN_CASE(ForceF64, 3, Q_F64, false, 2); }
+        } else return NB_ERR_UNSUPPORTED;
+    } else
+#undef NB_WIN_CASE
 #define NB_PHI_CASE(F, D, Q, U, UNR) rc = launch_accel<F<D, Q, IPT, TH, U, UNR, true>, 0>(a, workspace_bytes, st, &splits, &phi)
     if (want_phi) {
         if (dtype == NB_F32) {
@@ -1108,8 +1168,8 @@ extern "C" int nb_accel_window(const void* packed_src, int64_t n_src, int64_t fi
 extern "C" int nb_accel_finish(const void* workspace, int splits_total, int64_t n_tgt, int dim, int dtype, int mode, double G,
                                int uniform_mass, double mass_value, void* acc_out, void* stream) {
     if (!workspace || !acc_out || splits_total < 1 || n_tgt <= 0 || (dim != 2 && dim != 3)) return NB_ERR_INVALID_ARGUMENT;
-    if (mode != NB_MODE_FLOAT64 && mode != NB_MODE_FLOAT32 && mode != NB_MODE_FLOAT16 && mode != NB_MODE_BFLOAT16) return NB_ERR_UNSUPPORTED;
-    const bool uni = uniform_mass != 0 && ((dtype == NB_F32 && mode != NB_MODE_FLOAT64) || (dtype == NB_F64 && mode == NB_MODE_FLOAT64));
+    if (!((dtype == NB_F32 && mode == NB_MODE_FLOAT32) || (dtype == NB_F64 && mode == NB_MODE_FLOAT64))) return NB_ERR_UNSUPPORTED;
+    const bool uni = uniform_mass != 0;
     PartialSums p{};
     p.partial = (const double*)workspace;
     p.splits = splits_total;

@@ -31,7 +31,6 @@ from .quantization import PrecisionMode, levels_for_mode
 
 _INT_FORCE_SNAP = {PrecisionMode.INT8_SIM: 256, PrecisionMode.INT4_SIM: 16}
 _OVERLAP = os.environ.get("NB_B200_OVERLAP", "1") != "0"       # all-gather hidden behind the own-slot force window
-_WINDOW_MODES = (PrecisionMode.FLOAT64, PrecisionMode.FLOAT32, PrecisionMode.FLOAT16, PrecisionMode.BFLOAT16)
 
 
 class ShardPlan:
@@ -164,8 +163,8 @@ class ShardedGalaxySimulation:
     def pair_launches_next_tick(self) -> int:
         """How many pair-kernel launches the next tick's force evaluation makes (instrumentation: _lib.ForceTimer.arm)."""
         x = self.positions
-        windowed = self.world > 1 and _OVERLAP and self.precision_mode in _WINDOW_MODES and \
-            not (getattr(self, "_pe_wanted", False) and self._pe_fusable_dtype(torch.promote_types(x.dtype, self.accelerations.dtype)))
+        dt = torch.promote_types(x.dtype, self.accelerations.dtype)
+        windowed = self.world > 1 and _OVERLAP and self._pe_fusable_dtype(dt) and not getattr(self, "_pe_wanted", False)
         return 2 if windowed else 1
 
     def _force(self, x: torch.Tensor, emit: bool, local_packed: Optional[torch.Tensor] = None,
@@ -180,7 +179,8 @@ class ShardedGalaxySimulation:
         levels = levels_for_mode(mode) or 0
         n_src = plan.padded_sources if self.world > 1 else plan.slot_chunks * plan.chunk_sources
         self._pe_local = None
-        if self.world > 1 and _OVERLAP and mode in _WINDOW_MODES and not (want_pe and self._pe_fusable(x)):
+        # windowed launches (and the fused potential) exist for fp32 / FLOAT32 and fp64 / FLOAT64
+        if self.world > 1 and _OVERLAP and self._pe_fusable(x) and not want_pe:
             return self._force_windowed(x, local_packed, plan, n_src)
         packed = self._all_gather_packed(local_packed)
         self._last_packed, self._last_nsrc = packed, n_src
