@@ -155,14 +155,14 @@ int nb_accel_potential(const void* packed_src, int64_t n_src, const void* pos_tg
                        double mass_value, void* acc_out, double* pe_out, void* workspace, int64_t workspace_bytes,
                        void* stream);
 
-/* Windowed force evaluation for i-range-sharded ticks (fp32 state in FLOAT32 mode, fp64 state in FLOAT64 mode).  nb_accel_window streams the source chunks
- * [first_chunk, first_chunk + n_chunks) of the packed set — taken modulo ring_chunks when ring_chunks > 0, so a window may
- * wrap past the last chunk — and APPENDS its j-split partial sums to `workspace` behind the `splits_before` split slots
+/* Windowed force evaluation for i-range-sharded ticks (fp32 state in FLOAT32 mode, fp64 state in FLOAT64 mode).
+ * nb_accel_window streams the contiguous source chunks [first_chunk, first_chunk + n_chunks) of the packed set with the
+ * same kernels as nb_accel and APPENDS its j-split partial sums to `workspace` behind the `splits_before` split slots
  * earlier windows of the same evaluation wrote; *splits_total_out = splits_before + the slots it added (max_splits > 0 caps
- * them).  nb_accel_finish reduces all slots into acc_out exactly as nb_accel does.  A sharded tick runs the window of
- * the rank's OWN packed slot while the all-gather of the other ranks' slots is still in flight, then the ring window over
- * the remaining slots: the collective hides behind 1/P of the pair work. */
-int nb_accel_window(const void* packed_src, int64_t n_src, int64_t first_chunk, int64_t n_chunks, int64_t ring_chunks,
+ * them).  nb_accel_finish reduces all slots into acc_out exactly as nb_accel does.  A sharded tick runs the window of the
+ * rank's OWN packed slot while the all-gather of the other ranks' slots is still in flight, then the windows over the
+ * slots after and before its own: the collective hides behind 1/P of the pair work. */
+int nb_accel_window(const void* packed_src, int64_t n_src, int64_t first_chunk, int64_t n_chunks,
                     const void* pos_tgt, int64_t n_tgt, int dim, int dtype, int mode, double G, double eps_sq,
                     int uniform_mass, double mass_value, void* workspace, int64_t workspace_bytes, int splits_before,
                     int max_splits, int* splits_total_out, void* stream);

@@ -51,7 +51,7 @@ PROTOTYPES = {
                              c_double, c_int64, c_int, c_double, _P, _P, _P, _P, c_int64, c_int, _P, _P]),
     "nb_accel_potential": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_double, c_double, c_int, c_double,
                                    _P, _P, _P, c_int64, _P]),
-    "nb_accel_window": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, c_int, c_int, c_int, c_double, c_double, c_int,
+    "nb_accel_window": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, c_int, c_int, c_int, c_double, c_double, c_int,
                                 c_double, _P, c_int64, c_int, c_int, POINTER(c_int), _P]),
     "nb_accel_finish": (c_int, [_P, c_int, c_int64, c_int, c_int, c_int, c_double, c_int, c_double, _P, _P]),
     "nb_profile_next_force": (c_int, [_P, _P, c_int]),

@@ -44,9 +44,7 @@ enum QMode { Q_F32 = 0, Q_F16 = 1, Q_BF16 = 2, Q_LUT = 3, Q_F64 = 4, Q_LUTF = 5 
 
 struct AccelArgs {
     const char* src;          // packed sources
-    int64_t n_chunks;         // chunks this launch streams (the whole packed set, or a window of it)
-    int64_t chunk0;           // first chunk of the window
-    int64_t ring;             // > 0: chunk indices are taken modulo this (a window that wraps past the last chunk)
+    int64_t n_chunks;         // chunks this launch streams (the whole packed set, or a contiguous window of it starting at src)
     const void* pos_tgt;      // (n_tgt, DIM) state dtype
     int64_t n_tgt;
     int chunks_per_split;
@@ -364,6 +362,35 @@ struct ForceF32 {
             float2 zs = make_float2(0.f, 0.f), ms;
             if (DIM == 3) { const float4 b = B4[p]; zs = make_float2(b.x, b.y); ms = make_float2(b.z, b.w); }
             else ms = B2[p];
+#if NB_F32_ACC_VARIANT == 2
+            // Two phases per source pair: first the weights of ALL targets, then ALL accumulates.  With the accumulates of a
+            // target adjacent and nothing independent left to slot between them, ptxas keeps `w` in the operand-reuse cache
+            // for the 2nd and 3rd FFMA2 of each triple (2 issue cycles instead of 3: an FFMA2 reads three register PAIRS).
+            float2 wv[IPT], dxv[IPT], dyv[IPT], dzv[IPT];
+#pragma unroll
+            for (int t = 0; t < IPT; ++t) {
+                dxv[t] = add2(xs, nx[t]);
+                dyv[t] = add2(ys, ny[t]);
+                dzv[t] = DIM == 3 ? add2(zs, nz[t]) : make_float2(0.f, 0.f);
+                float2 d2 = dist_sq(dxv[t], dyv[t], dzv[t]);
+                if (QMODE == Q_LUT) {
+                    wv[t] = mul2(make_float2(lut_factor(d2.x), lut_factor(d2.y)), ms);
+                } else {
+                    if (QMODE == Q_F16) { const __half2 h = __floats2half2_rn(d2.x, d2.y); d2 = __half22float2(h); }
+                    else if (QMODE == Q_BF16) { const __nv_bfloat162 h = __floats2bfloat162_rn(d2.x, d2.y); d2 = __bfloat1622float2(h); }
+                    const float2 r = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
+                    wv[t] = ULOOP ? mul2(mul2(r, r), r) : mul2(mul2(r, r), mul2(r, ms));
+                    if (PHI) ap[t] = ULOOP ? add2(r, ap[t]) : fma2(ms, r, ap[t]);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < IPT; ++t) {
+                ax[t] = fma2(wv[t], dxv[t], ax[t]);
+                ay[t] = fma2(wv[t], dyv[t], ay[t]);
+                if (DIM == 3) az[t] = fma2(wv[t], dzv[t], az[t]);
+            }
+        }
+#else
 #pragma unroll
             for (int tt = 0; tt < IPT; ++tt) {
                 const int t = (NB_F32_PERTURB & 4) ? IPT - 1 - tt : tt;
@@ -424,6 +451,7 @@ struct ForceF32 {
 #endif
             }
         }
+#endif
         flush(chunk_mass);
     }
 
@@ -640,10 +668,7 @@ struct ForceMixed {       // fp32 sources/targets, FLOAT64 mode
 constexpr int kMaxLevelsSmem = 4096;      // level table entries staged in shared memory (64 KB + header)
 
 // LUTKIND: 0 = no level table, 1 = 16-byte entries replicated per bank group (Q_LUT), 2 = fast lookup (Q_LUTF)
-// WINDOW: the launch streams a window [chunk0, chunk0 + n_chunks) of the packed set, modulo `ring` (sharded ticks);
-// a template parameter so that the ordinary kernels keep exactly the code (and the ptxas schedule) they are tuned with —
-// the packed-FMA loop is register-bank limited and a different register assignment costs several per cent.
-template <class Consumer, int LUTKIND, bool WINDOW = false>
+template <class Consumer, int LUTKIND>
 __global__ void __launch_bounds__(Consumer::THREADS + 32, LUTKIND == 2 ? NB_LUTF_MINB : (Consumer::HAS_PHI ? 3 : 0)) accel_kernel(const AccelArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const bool is_consumer = threadIdx.x < Consumer::THREADS;
@@ -676,8 +701,7 @@ __global__ void __launch_bounds__(Consumer::THREADS + 32, LUTKIND == 2 ? NB_LUTF
     if constexpr (LUTKIND == 1) cons.levels_m1_f = (float)(a.levels - 1);
     const int64_t c0 = (int64_t)blockIdx.y * a.chunks_per_split;
     const int64_t c1 = min(a.n_chunks, c0 + (int64_t)a.chunks_per_split);
-    if constexpr (WINDOW) stream_sources(a.src, a.chunk0 + c0, a.chunk0 + c1, cons, a.ring);
-    else stream_sources(a.src, c0, c1, cons);
+    stream_sources(a.src, c0, c1, cons);
     if (is_consumer) cons.store(a, blockIdx.x, blockIdx.y);
 }
 
@@ -846,7 +870,7 @@ constexpr int64_t kPhiBlockBytes = 16 * 1024;        // per-CTA partial sums of 
 struct ForceProfile { void* start; void* stop; int launches; };       // stop is recorded after the `launches`-th launch
 inline ForceProfile& force_profile() { static thread_local ForceProfile p{nullptr, nullptr, 0}; return p; }
 
-template <class Consumer, int LUTKIND, bool WINDOW = false>
+template <class Consumer, int LUTKIND>
 int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, int* splits_out, double** phi_out = nullptr) {
     AccelArgs a = a0;
     // a windowed launch appends its split slots behind the ones earlier windows of the same evaluation wrote
@@ -869,7 +893,7 @@ int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, 
         const int P = lut_pow2ceil(a.levels);
         smem += P * 128 + (P + 1 + 3) / 4 * 16;
     }
-    auto kern = accel_kernel<Consumer, LUTKIND, WINDOW>;
+    auto kern = accel_kernel<Consumer, LUTKIND>;
     int ctas_per_sm = 1;
     const int frc = kernel_occupancy((const void*)kern, Consumer::THREADS + 32, smem, &ctas_per_sm);
     if (frc != NB_OK) return frc;
@@ -917,33 +941,19 @@ int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, 
     AccelArgs a{};
     a.src = (const char*)packed_src;
     a.n_chunks = nb_num_chunks(n_src, dtype);
-    // developer A/B switch (tools/time_splits.py): run ordinary launches through the WINDOW instantiation, whose ptxas schedule
-    // differs (operand-reuse flags in the packed-FMA loop), over the whole source set
-    static const bool force_window_kernel = [] { const char* e = getenv("NB_B200_WINDOW_KERNEL"); return e && atoi(e) != 0; }();
-    SourceWindow whole{0, a.n_chunks, 0, 0, 0};
-    if (!window && force_window_kernel && !lut && !want_phi &&
-        ((dtype == NB_F32 && mode == NB_MODE_FLOAT32) || (dtype == NB_F64 && mode == NB_MODE_FLOAT64)))
-        window = &whole;
     if (window) {
-        // a window of the packed set [first, first + count), modulo ring_chunks when the window wraps (float modes only)
-        if (lut || want_phi || window->first_chunk < 0 || window->n_chunks <= 0 || window->splits_before < 0) return NB_ERR_INVALID_ARGUMENT;
-        const int64_t limit = window->ring_chunks > 0 ? window->ring_chunks : a.n_chunks;
-        if (window->ring_chunks > a.n_chunks || window->n_chunks > limit || (window->ring_chunks <= 0 && window->first_chunk + window->n_chunks > limit))
+        // a contiguous window [first, first + count) of the packed set: the SAME kernels, started at an offset source pointer
+        // (one kernel image for single- and multi-GPU runs: the packed-FMA loop's ptxas schedule is worth several per cent
+        // and differs between otherwise equivalent instantiations — profiles/r02/README.md)
+        if (lut || want_phi || window->first_chunk < 0 || window->n_chunks <= 0 || window->splits_before < 0 ||
+            window->first_chunk + window->n_chunks > a.n_chunks)
             return NB_ERR_INVALID_ARGUMENT;
-        a.chunk0 = window->first_chunk;
+        if (!((dtype == NB_F32 && mode == NB_MODE_FLOAT32) || (dtype == NB_F64 && mode == NB_MODE_FLOAT64))) return NB_ERR_UNSUPPORTED;
+        a.src += window->first_chunk * (int64_t)chunk_bytes(dim);
         a.n_chunks = window->n_chunks;
-        a.ring = window->ring_chunks > 0 ? window->ring_chunks : 0;
         a.splits_before = window->splits_before;
         a.max_splits = window->max_splits;
     }
-    a.pos_tgt = pos_tgt;
-    a.n_tgt = n_tgt;
-    a.partial = (double*)workspace;
-    a.eps_sq = eps_sq;
-    a.table = level_table;
-    a.levels = levels;
-    a.neg_zero = -0.0f;
-    a.uniform_mass = (lut && levels <= kLutFastMaxLevels && uniform_mass != 0 && mass_value != 0.0) ? (float)mass_value : 0.f;
 
     int splits = 0, rc = NB_ERR_INVALID_ARGUMENT;
     double* phi = nullptr;
@@ -954,18 +964,6 @@ int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, 
 #define NB_F32_UNI_CASE(D, Q) rc = launch_accel<ForceF32<D, Q, IPT, TH, true>, 0>(a, workspace_bytes, st, &splits)
 #define NB_F32_CASE(D, Q, LUT) rc = launch_accel<ForceF32<D, Q, IPT, TH>, LUT>(a, workspace_bytes, st, &splits)
 #define NB_F64_CASE(D, Q) rc = launch_accel<ForceF64<D, Q, IPT, TH>, 0>(a, workspace_bytes, st, &splits)
-#define NB_WIN_CASE(F, D, Q, U, UNR) rc = launch_accel<F<D, Q, IPT, TH, U, UNR>, 0, true>(a, workspace_bytes, st, &splits)
-    if (window) {
-        // windowed launches exist where the pair loop sees the state dtype's own d²: fp32 / FLOAT32 and fp64 / FLOAT64
-        if (dtype == NB_F32 && mode == NB_MODE_FLOAT32) {
-            if (uni) { if (dim == 2) NB_WIN_CASE(ForceF32, 2, Q_F32, true, 4); else NB_WIN_CASE(ForceF32, 3, Q_F32, true, 4); }
-            else { if (dim == 2) NB_WIN_CASE(ForceF32, 2, Q_F32, false, 4); else NB_WIN_CASE(ForceF32, 3, Q_F32, false, 4); }
-        } else if (dtype == NB_F64 && mode == NB_MODE_FLOAT64) {
-            if (uni) { if (dim == 2) NB_WIN_CASE(ForceF64, 2, Q_F64, true, 2); else NB_WIN_CASE(ForceF64, 3, Q_F64, true, 2); }
-            else { if (dim == 2) NB_WIN_CASE(ForceF64, 2, Q_F64, false, 2); else NB_WIN_CASE(ForceF64, 3, Q_F64, false, 2); }
-        } else return NB_ERR_UNSUPPORTED;
-    } else
-#undef NB_WIN_CASE
 #define NB_PHI_CASE(F, D, Q, U, UNR) rc = launch_accel<F<D, Q, IPT, TH, U, UNR, true>, 0>(a, workspace_bytes, st, &splits, &phi)
     if (want_phi) {
         if (dtype == NB_F32) {
@@ -1150,14 +1148,14 @@ extern "C" int nb_accel(const void* packed_src, int64_t n_src, const void* pos_t
 }
 
 // Windowed evaluation (i-range-sharded ticks): the window of the rank's OWN packed slot runs while the all-gather of the
-// other slots is still in flight, then the ring window over the remaining slots; nb_accel_finish reduces both.
-extern "C" int nb_accel_window(const void* packed_src, int64_t n_src, int64_t first_chunk, int64_t n_chunks, int64_t ring_chunks,
+// other slots is still in flight, then the windows over the slots after and before it; nb_accel_finish reduces them all.
+extern "C" int nb_accel_window(const void* packed_src, int64_t n_src, int64_t first_chunk, int64_t n_chunks,
                                const void* pos_tgt, int64_t n_tgt, int dim, int dtype, int mode, double G, double eps_sq,
                                int uniform_mass, double mass_value, void* workspace, int64_t workspace_bytes, int splits_before,
                                int max_splits, int* splits_total_out, void* stream) {
     if (!splits_total_out) return NB_ERR_INVALID_ARGUMENT;
     PartialSums p{};
-    const SourceWindow w{first_chunk, n_chunks, ring_chunks, splits_before, max_splits};
+    const SourceWindow w{first_chunk, n_chunks, splits_before, max_splits};
     const int rc = accel_pairs(packed_src, n_src, pos_tgt, n_tgt, dim, dtype, mode, G, eps_sq, nullptr, 0, uniform_mass, mass_value,
                                nullptr, workspace, workspace_bytes, (cudaStream_t)stream, &p, false, &w);
     if (rc != NB_OK) return rc;

@@ -20,8 +20,8 @@ struct PartialSums {
     int64_t n_tgt;
 };
 
-// a window of the packed source set: chunks [first_chunk, first_chunk + n_chunks), modulo ring_chunks when > 0
-struct SourceWindow { int64_t first_chunk, n_chunks, ring_chunks; int splits_before, max_splits; };
+// a contiguous window of the packed source set: chunks [first_chunk, first_chunk + n_chunks)
+struct SourceWindow { int64_t first_chunk, n_chunks; int splits_before, max_splits; };
 
 int accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, int64_t n_tgt, int dim, int dtype, int mode,
                 double G, double eps_sq, const void* level_table, int levels, int uniform_mass, double mass_value,

@@ -104,7 +104,7 @@ class CudaOps:
         n, dim = x_tgt.shape
         return self._scratch("accel", self.lib.nb_accel_workspace_bytes(n, dim), x_tgt.device)
 
-    def accel_window(self, packed, n_src, first_chunk, n_chunks, ring_chunks, x_tgt, mode: str, G, eps_sq, uniform=(False, 0.0),
+    def accel_window(self, packed, n_src, first_chunk, n_chunks, x_tgt, mode: str, G, eps_sq, uniform=(False, 0.0),
                      splits_before=0, max_splits=0) -> int:
         """One window of a windowed force evaluation (nb_accel_window); returns the split slots used so far."""
         L.require_cuda(packed, x_tgt)
@@ -112,7 +112,7 @@ class CudaOps:
         ws = self._scratch("accel", self.lib.nb_accel_workspace_bytes(n, dim), x_tgt.device)
         total = ctypes.c_int(0)
         with torch.cuda.device(x_tgt.device):
-            L.check(self.lib.nb_accel_window(L.ptr(packed), int(n_src), int(first_chunk), int(n_chunks), int(ring_chunks),
+            L.check(self.lib.nb_accel_window(L.ptr(packed), int(n_src), int(first_chunk), int(n_chunks),
                                              L.ptr(x_tgt), n, dim, L.dtype_code(x_tgt), L.MODE_CODES[mode], float(G), float(eps_sq),
                                              int(bool(uniform[0])), float(uniform[1]), L.ptr(ws), ws.numel(), int(splits_before),
                                              int(max_splits), ctypes.byref(total), L.stream_ptr(x_tgt.device)), "nb_accel_window")

@@ -165,7 +165,7 @@ class ShardedGalaxySimulation:
         x = self.positions
         dt = torch.promote_types(x.dtype, self.accelerations.dtype)
         windowed = self.world > 1 and _OVERLAP and self._pe_fusable_dtype(dt) and not getattr(self, "_pe_wanted", False)
-        return 2 if windowed else 1
+        return 1 + (self.rank > 0) + (self.rank < self.world - 1) if windowed else 1
 
     def _force(self, x: torch.Tensor, emit: bool, local_packed: Optional[torch.Tensor] = None,
                want_pe: bool = False) -> torch.Tensor:
@@ -204,30 +204,36 @@ class ShardedGalaxySimulation:
 
     def _force_windowed(self, x, local_packed, plan, n_src):
         """Float modes on several ranks.  Compute stream: the pair kernel over this rank's OWN slot (1/P of the work)
-        starts at once.  Side stream: the in-place all-gather of the other slots, then the pair kernel over those P−1
-        slots in ring order.  The two launches run concurrently (the hardware fills the tail of one with the other); one
+        starts at once.  Side stream: the in-place all-gather of the other slots, then the pair kernel over the slots
+        after and before this rank's (two contiguous windows, the same kernel image as a single-GPU run).  The launches
+        of the two streams run concurrently (the hardware fills the tail of one with the other); one
         reduction over the split slots of both follows on the compute stream."""
         ops, mode, uni = self.ops, self.precision_mode.value, self._uniform_mass()
         slot = plan.slot_chunks
-        first, rest = (self.rank * slot, slot, 0), ((self.rank + 1) * slot, (self.world - 1) * slot, self.world * slot)
+        own = (self.rank * slot, slot)
+        # the other slots as contiguous windows: the ones after this rank's, then the ones before it
+        others = [w for w in (((self.rank + 1) * slot, (self.world - 1 - self.rank) * slot), (0, self.rank * slot)) if w[1] > 0]
+        kw = dict(uniform=uni)
         if not x.is_cuda:                        # CPU test backends: same windows, no streams
             packed = self._all_gather_packed(local_packed)
             self._last_packed, self._last_nsrc = packed, n_src
-            used = ops.accel_window(packed, n_src, *first, x, mode, self.G, self.softening_sq, uniform=uni, splits_before=0, max_splits=6)
-            used = ops.accel_window(packed, n_src, *rest, x, mode, self.G, self.softening_sq, uniform=uni, splits_before=used)
+            used = ops.accel_window(packed, n_src, *own, x, mode, self.G, self.softening_sq, splits_before=0, max_splits=6, **kw)
+            for w in others:
+                used = ops.accel_window(packed, n_src, *w, x, mode, self.G, self.softening_sq, splits_before=used, **kw)
             return ops.accel_finish(used, x, mode, self.G, uniform=uni)
         main, side = torch.cuda.current_stream(self.device), self._side_stream()
         packed = self._packed_all
         self._last_packed, self._last_nsrc = packed, n_src
-        ops.accel_workspace(x)                   # allocate the shared scratch on the compute stream before either launch
+        ops.accel_workspace(x)                   # allocate the shared scratch on the compute stream before any launch
         ready = torch.cuda.Event()
         ready.record(main)                       # the KDK kernel has written this rank's slot
-        used = ops.accel_window(packed, n_src, *first, x, mode, self.G, self.softening_sq, uniform=uni, splits_before=0, max_splits=6)
+        used = ops.accel_window(packed, n_src, *own, x, mode, self.G, self.softening_sq, splits_before=0, max_splits=6, **kw)
         done = torch.cuda.Event()
         with torch.cuda.stream(side):
             side.wait_event(ready)
             self._all_gather_packed(local_packed)
-            used = ops.accel_window(packed, n_src, *rest, x, mode, self.G, self.softening_sq, uniform=uni, splits_before=used)
+            for w in others:
+                used = ops.accel_window(packed, n_src, *w, x, mode, self.G, self.softening_sq, splits_before=used, **kw)
             done.record(side)
         main.wait_event(done)
         return ops.accel_finish(used, x, mode, self.G, uniform=uni)

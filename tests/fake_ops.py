@@ -153,14 +153,12 @@ class FakeOps:
             scalars[L.SLOT_ACC_MAX] = max(int(scalars[L.SLOT_ACC_MAX]), key(acc.max().item()))
         return acc
 
-    def accel_window(self, packed, n_src, first_chunk, n_chunks, ring_chunks, x_tgt, mode, G, eps_sq, uniform=(False, 0.0),
+    def accel_window(self, packed, n_src, first_chunk, n_chunks, x_tgt, mode, G, eps_sq, uniform=(False, 0.0),
                      splits_before=0, max_splits=0):
-        """Partial accelerations of one source window (chunks taken modulo ring_chunks when > 0), kept per slot."""
+        """Partial accelerations of one contiguous source window, kept per slot."""
         cs = self.chunk_sources(x_tgt.dtype)
         pos, m = self.unpack(packed, n_src, x_tgt.shape[1], x_tgt.dtype)
         idx = torch.arange(first_chunk, first_chunk + n_chunks)
-        if ring_chunks > 0:
-            idx = idx % ring_chunks
         sel = (idx.unsqueeze(1) * cs + torch.arange(cs).unsqueeze(0)).reshape(-1)
         diff = pos[sel].unsqueeze(0) - x_tgt.unsqueeze(1)
         d2 = (diff ** 2).sum(dim=-1) + eps_sq
