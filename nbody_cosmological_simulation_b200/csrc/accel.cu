@@ -873,6 +873,7 @@ inline ForceProfile& force_profile() { static thread_local ForceProfile p{nullpt
 template <class Consumer, int LUTKIND>
 int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, int* splits_out, double** phi_out = nullptr) {
     AccelArgs a = a0;
+    if (a.n_tgt <= 0 || a.n_chunks <= 0 || !a.partial) return NB_ERR_INVALID_ARGUMENT;
     // a windowed launch appends its split slots behind the ones earlier windows of the same evaluation wrote
     const int splits_before = a.splits_before;
     a.partial += (int64_t)splits_before * a.n_tgt * Consumer::DIM;
@@ -954,6 +955,14 @@ int nb::accel_pairs(const void* packed_src, int64_t n_src, const void* pos_tgt, 
         a.splits_before = window->splits_before;
         a.max_splits = window->max_splits;
     }
+    a.pos_tgt = pos_tgt;
+    a.n_tgt = n_tgt;
+    a.partial = (double*)workspace;
+    a.eps_sq = eps_sq;
+    a.table = level_table;
+    a.levels = levels;
+    a.neg_zero = -0.0f;
+    a.uniform_mass = (lut && levels <= kLutFastMaxLevels && uniform_mass != 0 && mass_value != 0.0) ? (float)mass_value : 0.f;
 
     int splits = 0, rc = NB_ERR_INVALID_ARGUMENT;
     double* phi = nullptr;

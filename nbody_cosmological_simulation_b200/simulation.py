@@ -422,8 +422,10 @@ class GalaxySimulation:
 
     # below this many particles a tick is launch-latency bound: replay it from a CUDA graph ...
     GRAPH_MAX_STARS = 65536
-    # ... and below this many, run whole spans of ticks as ONE persistent cooperative kernel (fp32 state, FLOAT32 mode)
-    PERSISTENT_MAX_STARS = 16384
+    # ... and below this many, run whole spans of ticks as ONE persistent cooperative kernel (fp32 state, FLOAT32 mode):
+    # measured 9.1 / 12.3 / 14.8 us per tick at N = 500 / 1000 / 3000 against 12.4 / 14.4 / 16.4 from the graph, but 58 vs 47
+    # at N = 10 000 (two resident CTAs per SM instead of three) — profiles/r02/README.md
+    PERSISTENT_MAX_STARS = 4096
 
     def _run_fused(self, ticks: int, spec=None):
         """`ticks` stock ticks in ONE native call (nb_run_ticks): the closing half kick of tick t is fused into the

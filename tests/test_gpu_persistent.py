@@ -25,8 +25,9 @@ def _system(n, dim, uniform, seed=3):
 
 @pytest.mark.parametrize("n,dim,uniform", [(500, 2, True), (3000, 2, True), (3000, 3, False), (10000, 2, True), (700, 3, False),
                                            (16384, 3, True), (257, 2, False), (5121, 3, True)])
-def test_persistent_run_is_bit_identical_to_single_ticks(n, dim, uniform):
+def test_persistent_run_is_bit_identical_to_single_ticks(n, dim, uniform, monkeypatch):
     import nbody_cosmological_simulation_b200 as nb
+    monkeypatch.setattr(nb.GalaxySimulation, "PERSISTENT_MAX_STARS", 16384)       # exercise the kernel beyond its default range too
     args = _system(n, dim, uniform)
     a = nb.GalaxySimulation(*args, precision_mode=nb.PrecisionMode.FLOAT32)
     b = nb.GalaxySimulation(*args, precision_mode=nb.PrecisionMode.FLOAT32)

@@ -257,9 +257,10 @@ def test_int_mode_general_masses_mismatches_are_boundary_flips():
 # ---------------------------------------------------------------------------------------------------
 # BASELINE configs[0]: main.py --stars N --ticks 2000 --compare float64,int4 (golden from the reference, N = 2000)
 # ---------------------------------------------------------------------------------------------------
-@pytest.fixture(scope="module")
-def c1():
-    return np.load(os.path.join(GOLDEN, "c1_disk2000.npz"))
+@pytest.fixture(scope="module", params=["c1_disk2000", "c1_disk5000"])
+def c1(request):
+    """N = 2000 and N = 5000 (the size BASELINE.json configs[0] states), both 2000 ticks, recorded from the reference."""
+    return np.load(os.path.join(GOLDEN, request.param + ".npz"))
 
 
 def _run_c1(c1, mode):
@@ -300,7 +301,7 @@ def test_c1_float64_energy_series_tick_by_tick(c1):
     # the remaining collect_metrics outputs along the same trajectory (f1)
     np.testing.assert_allclose(m.galaxy_radius_90, c1["float64/radius90"], rtol=1e-5)
     np.testing.assert_allclose(m.velocity_dispersion, c1["float64/dispersion"], rtol=1e-5)
-    np.testing.assert_allclose(m.bound_fraction, c1["float64/bound"], atol=1.01 / 2000)       # one star on the v_esc edge
+    np.testing.assert_allclose(m.bound_fraction, c1["float64/bound"], atol=2.01 / len(c1["mass"]))      # a star or two on the v_esc edge
     np.testing.assert_array_equal(m.rotation_curves[-1]["num_stars_per_bin"], c1["float64/rc_final_cnt"])
 
 

@@ -174,3 +174,17 @@ def test_tables_present():
         t = json.load(f)
     assert t["mode_from_string"]["nonsense"] == "float64"       # unknown strings fall back silently
     assert set(t["enum"].values()) == set(ALL_MODES)
+
+
+def test_c1_fixture_first_ticks(golden):
+    """BASELINE configs[0] fixture (tests/golden/make_golden_c1.py, N = 2000): the oracle replays the first 20 ticks of both
+    modes and lands on the recorded total energies (the full 2000-tick series is compared on the GPU)."""
+    g = golden("c1_disk2000")
+    pos, vel, mass = (torch.from_numpy(g[k]) for k in ("pos", "vel", "mass"))
+    for mode, tol in (("float64", 1e-9), ("int4_sim", 2e-6)):
+        st = ora.State(pos, vel, mass, mode=mode)
+        assert abs(st.total() - g[f"{mode}/early_total"][0]) <= tol * abs(g[f"{mode}/early_total"][0])
+        for k in (1, 2):
+            st.run(10)
+            assert int(g[f"{mode}/early_ticks"][k]) == st.tick
+            assert abs(st.total() - g[f"{mode}/early_total"][k]) <= tol * abs(g[f"{mode}/early_total"][k]), (mode, k)
