@@ -858,6 +858,117 @@ __global__ void __launch_bounds__(Consumer::THREADS + 32, 2) persistent_ticks_ke
     }
 }
 
+// ======================================================================================================
+// One-barrier ticks for the smallest systems (N <= 4096)
+// ======================================================================================================
+// persistent_ticks_kernel pays two grid barriers per tick and the start-up of the TMA ring in every force phase.  Here a
+// tick has ONE barrier: CTA (tile, split) integrates the particles it needs ITSELF — its 256 targets and the 256·cps
+// sources of its split — from the previous state (x, v ping-pong buffers; Σ_j sums in three rotating fp64 buffers), puts
+// the source records into shared memory in the packed layout, runs the same pair loop as every other force kernel
+// (ForceF32::chunk on shared memory), and adds its per-target sums to the fp64 buffer with atomics.  The integrator is
+// redone by every CTA that needs a particle (≈ 2·cps+... particle updates per thread), which is cheaper than a second
+// barrier; the CTAs of split 0 own the tile and write its new state.  fp64 atomic adds of fp32-valued chunk sums are exact
+// (24-bit mantissas, tens of addends), so their order cannot change the result: runs are bit-identical to the kernels
+// issued one by one.  Three sum buffers: tick t reads A, adds into B and clears C (read in tick t−1, idle now).
+struct SmallTicksArgs {
+    float* xv[2][2];             // [buffer][0 = x, 1 = v]; buffer 0 is the caller's state
+    float* acc;                  // accelerations (float), written with the final state
+    double* sums[3];             // rotating Σ_j buffers, n·DIM doubles each
+    const double* partial_in; int splits_in;     // partial sums of the force pass that preceded the launch (tick 0 reads these)
+    const void* mass; int mass_f64;
+    int64_t n; int ticks, tiles, splits, cps; int64_t n_chunks;
+    float half_dt, dt, eps_sq, neg_zero; double scale;
+};
+
+template <int DIM, bool UNI>
+__global__ void __launch_bounds__(256, 1) small_ticks_kernel(const SmallTicksArgs p) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(128) unsigned char smem[];
+    using Cons = ForceF32<DIM, Q_F32, 1, 256, UNI>;
+    const int tile = (int)(blockIdx.x % p.tiles), split = (int)(blockIdx.x / p.tiles);
+    const bool active = (int)blockIdx.x < p.tiles * p.splits;
+    const bool owner = active && split == 0;
+    const int64_t tgt = (int64_t)tile * 256 + threadIdx.x;
+    const int64_t count = p.n * DIM;
+    const int cb = chunk_bytes(DIM);
+    const int64_t c0 = (int64_t)split * p.cps, c1 = min(p.n_chunks, c0 + (int64_t)p.cps);
+
+    // state of particle i after this tick's kick(s) and drift, from the previous state and its Σ_j sums
+    auto advance = [&](int64_t i, int t, const float* x, const float* v, const double* sums, float* xo, float* vo, float* ao) {
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) {
+            const int64_t e = i * DIM + k;
+            double sacc;
+            // (other SMs rewrite these buffers every second / third tick: read them past the non-coherent L1)
+            if (t == 0) { sacc = 0.0; for (int sp = 0; sp < p.splits_in; ++sp) sacc += p.partial_in[(int64_t)sp * count + e]; }
+            else sacc = __ldcg(sums + e);
+            const float a = (float)(sacc * p.scale);
+            const float kick = __fmul_rn(a, p.half_dt);
+            float vn = __fadd_rn(__ldcg(v + e), kick);            // simulation.py:141 (closing kick of the previous tick)
+            vn = __fadd_rn(vn, kick);                             // :132 (opening kick)
+            xo[k] = __fadd_rn(__ldcg(x + e), __fmul_rn(vn, p.dt));   // :135
+            vo[k] = vn;
+            ao[k] = a;
+        }
+    };
+
+    for (int t = 0; t < p.ticks; ++t) {
+        const float* x = p.xv[t & 1][0];
+        const float* v = p.xv[t & 1][1];
+        float* xn = p.xv[(t + 1) & 1][0];
+        float* vn = p.xv[(t + 1) & 1][1];
+        const double* s_read = p.sums[t % 3];
+        double* s_add = p.sums[(t + 1) % 3];
+        double* s_clear = p.sums[(t + 2) % 3];
+        if (active) {
+            Cons cons;
+            // --- own target: integrate, keep the new position in registers; the tile's owner CTA writes the new state
+            float xt[3] = {0.f, 0.f, 0.f}, vt[3], at[3];
+            const int64_t ti = tgt < p.n ? tgt : p.n - 1;
+            advance(ti, t, x, v, s_read, xt, vt, at);
+            if (owner && tgt < p.n) {
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) { xn[tgt * DIM + k] = xt[k]; vn[tgt * DIM + k] = vt[k]; p.acc[tgt * DIM + k] = at[k]; s_clear[tgt * DIM + k] = 0.0; }
+            }
+            cons.nx[0] = make_float2(-xt[0], -xt[0]); cons.ny[0] = make_float2(-xt[1], -xt[1]); cons.nz[0] = make_float2(-xt[2], -xt[2]);
+            cons.ax[0] = cons.ay[0] = cons.az[0] = make_float2(0.f, 0.f);
+            cons.sx[0] = cons.sy[0] = cons.sz[0] = 0.0;
+            cons.eps2 = make_float2(p.eps_sq, p.eps_sq);
+            cons.neg_zero = p.neg_zero;
+            // --- the sources of this split: integrate and write their packed records into shared memory
+            for (int64_t c = c0; c < c1; ++c) {
+                const int64_t sidx = c * 256 + threadIdx.x;
+                float xs[3] = {kPadCoordF32, kPadCoordF32, kPadCoordF32}, vs[3], as[3], ms = 0.f;
+                if (sidx < p.n) {
+                    advance(sidx, t, x, v, s_read, xs, vs, as);
+                    ms = p.mass_f64 ? (float)reinterpret_cast<const double*>(p.mass)[sidx] : reinterpret_cast<const float*>(p.mass)[sidx];
+                }
+                float* A = reinterpret_cast<float*>(smem + (c - c0) * cb);
+                float* B = reinterpret_cast<float*>(smem + (c - c0) * cb + kChunkABytes);
+                const int u = threadIdx.x >> 1, h = threadIdx.x & 1;
+                A[u * 4 + h] = xs[0]; A[u * 4 + 2 + h] = xs[1];
+                if (DIM == 3) { B[u * 4 + h] = xs[2]; B[u * 4 + 2 + h] = ms; }
+                else B[u * 2 + h] = ms;
+            }
+            __syncthreads();
+            for (int64_t c = c0; c < c1; ++c) cons.chunk(smem + (c - c0) * cb, c);
+            if (tgt < p.n) {
+                atomicAdd(&s_add[tgt * DIM + 0], cons.sx[0]);
+                atomicAdd(&s_add[tgt * DIM + 1], cons.sy[0]);
+                if (DIM == 3) atomicAdd(&s_add[tgt * DIM + 2], cons.sz[0]);
+            }
+        }
+        __threadfence();
+        grid.sync();
+    }
+    // the state of the last tick is in buffer (ticks & 1): bring it home if that is the scratch buffer (no CTA reads it any more)
+    if ((p.ticks & 1) && owner && tgt < p.n) {
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) { p.xv[0][0][tgt * DIM + k] = p.xv[1][0][tgt * DIM + k]; p.xv[0][1][tgt * DIM + k] = p.xv[1][1][tgt * DIM + k]; }
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------
 constexpr int kForceThreads = 256;
 constexpr int kForceIPT = 2;
@@ -1089,12 +1200,79 @@ static int launch_persistent(PersistentArgs& p, int64_t workspace_bytes, cudaStr
     return NB_OK;
 }
 
+// One-barrier ticks (small_ticks_kernel): same contract as persistent_ticks below; N <= 4096.
+template <int DIM, bool UNI>
+static int launch_small_ticks(SmallTicksArgs& p, cudaStream_t st) {
+    auto kern = small_ticks_kernel<DIM, UNI>;
+    const int smem = p.cps * chunk_bytes(DIM);
+    int occ = 0;
+    const int frc = kernel_occupancy((const void*)kern, 256, smem, &occ);
+    if (frc != NB_OK) return frc;
+    const int grid = p.tiles * p.splits;
+    if (grid > device_sm_count() * occ) return NB_ERR_UNSUPPORTED;
+    void* params[] = {(void*)&p};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(256), params, (size_t)smem, st);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources) {
+        cudaGetLastError();
+        return NB_ERR_UNSUPPORTED;
+    }
+    return e == cudaSuccess ? NB_OK : cuda_status(e);
+}
+
+static int small_ticks(void* x, void* v, void* acc, const void* mass, int mass_dtype, int64_t n, int dim, double G, double eps_sq,
+                       double dt, int uniform_mass, double mass_value, void* workspace, int64_t workspace_bytes, int64_t ticks,
+                       PartialSums* ps, cudaStream_t st) {
+    if (n > 4096 || ticks > 0x7fffffff) return NB_ERR_UNSUPPORTED;
+    const bool uni = uniform_mass != 0;
+    const int64_t count = n * dim;
+    SmallTicksArgs p{};
+    p.n = n; p.ticks = (int)ticks;
+    p.n_chunks = nb_num_chunks(n, NB_F32);
+    p.tiles = (int)((n + 255) / 256);
+    int max_splits = device_sm_count() / p.tiles;                     // one CTA per SM
+    if (max_splits < 1) return NB_ERR_UNSUPPORTED;
+    if (max_splits > p.n_chunks) max_splits = (int)p.n_chunks;
+    p.cps = (int)((p.n_chunks + max_splits - 1) / max_splits);
+    p.splits = (int)((p.n_chunks + p.cps - 1) / p.cps);
+    // scratch behind the partial sums the launch starts from: three fp64 sum buffers + the second x, v buffer
+    const int64_t in_bytes = (int64_t)ps->splits * count * (int64_t)sizeof(double);
+    const int64_t need = in_bytes + 3 * count * (int64_t)sizeof(double) + 2 * count * (int64_t)sizeof(float) + 256;
+    if (workspace_bytes < need) return NB_ERR_UNSUPPORTED;
+    char* base = (char*)workspace + ((in_bytes + 127) / 128) * 128;
+    for (int b = 0; b < 3; ++b) p.sums[b] = (double*)(base + b * count * (int64_t)sizeof(double));
+    float* x1 = (float*)(base + 3 * count * (int64_t)sizeof(double));
+    p.xv[0][0] = (float*)x; p.xv[0][1] = (float*)v; p.xv[1][0] = x1; p.xv[1][1] = x1 + count;
+    p.acc = (float*)acc;
+    p.partial_in = ps->partial; p.splits_in = ps->splits;
+    p.mass = mass; p.mass_f64 = mass_dtype == NB_F64;
+    p.half_dt = (float)(dt / 2); p.dt = (float)dt; p.eps_sq = (float)eps_sq; p.neg_zero = -0.0f;
+    p.scale = uni ? G * mass_value : G;
+    if (ps->scale != p.scale || ps->count != count) return NB_ERR_UNSUPPORTED;
+    // tick 0 adds into sums[1], tick 1 into sums[2] (cleared by tick 0's owners), ...: only sums[1] must start at zero
+    cudaError_t e = cudaMemsetAsync(p.sums[1], 0, count * sizeof(double), st);
+    if (e != cudaSuccess) return cuda_status(e);
+    int rc;
+    if (dim == 2) rc = uni ? launch_small_ticks<2, true>(p, st) : launch_small_ticks<2, false>(p, st);
+    else rc = uni ? launch_small_ticks<3, true>(p, st) : launch_small_ticks<3, false>(p, st);
+    if (rc != NB_OK) return rc;
+    // the sums of the last force pass: one "split"
+    ps->partial = p.sums[ticks % 3];
+    ps->splits = 1;
+    return NB_OK;
+}
+
 int nb::persistent_ticks(void* x, void* v, void* acc, const void* mass, int mass_dtype, int64_t n, int dim, int dtype, int mode, double G,
                          double eps_sq, double dt, int uniform_mass, double mass_value, void* packed, void* workspace,
                          int64_t workspace_bytes, int64_t ticks, PartialSums* ps, cudaStream_t st) {
     if (dtype != NB_F32 || mode != NB_MODE_FLOAT32 || ticks < 1 || ticks > 0x7fffffff || n > 32768 || !ps || !ps->partial ||
         ps->out_f64 || ps->minmax)
         return NB_ERR_UNSUPPORTED;
+    static const bool one_barrier = [] { const char* e = getenv("NB_B200_ONE_BARRIER"); return !e || atoi(e) != 0; }();
+    if (one_barrier && n <= 4096) {
+        const int rc = small_ticks(x, v, acc, mass, mass_dtype, n, dim, G, eps_sq, dt, uniform_mass, mass_value, workspace, workspace_bytes,
+                                   ticks, ps, st);
+        if (rc != NB_ERR_UNSUPPORTED) return rc;
+    }
     const bool uni = uniform_mass != 0;
     PersistentArgs p{};
     p.a.src = (const char*)packed;

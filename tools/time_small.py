@@ -4,7 +4,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nbody_cosmological_simulation_b200 as nb
 dev = torch.device("cuda:0")
-for n in (500, 1000, 3000, 10000, 16384):
+for n in (500, 1000, 2000, 3000, 4096, 10000):
     for dim in (2,):
         torch.manual_seed(0)
         p, v, m = nb.create_disk_galaxy(n, device=dev)
