@@ -204,10 +204,10 @@ class ShardedGalaxySimulation:
 
     def _force_windowed(self, x, local_packed, plan, n_src):
         """Float modes on several ranks.  Compute stream: the pair kernel over this rank's OWN slot (1/P of the work)
-        starts at once.  Side stream: the in-place all-gather of the other slots, then the pair kernel over the slots
-        after and before this rank's (two contiguous windows, the same kernel image as a single-GPU run).  The launches
-        of the two streams run concurrently (the hardware fills the tail of one with the other); one
-        reduction over the split slots of both follows on the compute stream."""
+        starts at once.  Side stream: the in-place all-gather of the other slots.  Compute stream again, once the gather
+        is done: the pair kernel over the slots after and before this rank's (two contiguous windows, the same kernel image
+        as a single-GPU run).  (Launching those on the side stream too, so that they overlap the tail of the first window,
+        hung on 2 GPUs in session E and was withdrawn.)  One reduction over the split slots of all windows follows."""
         ops, mode, uni = self.ops, self.precision_mode.value, self._uniform_mass()
         slot = plan.slot_chunks
         own = (self.rank * slot, slot)
@@ -217,25 +217,24 @@ class ShardedGalaxySimulation:
         if not x.is_cuda:                        # CPU test backends: same windows, no streams
             packed = self._all_gather_packed(local_packed)
             self._last_packed, self._last_nsrc = packed, n_src
-            used = ops.accel_window(packed, n_src, *own, x, mode, self.G, self.softening_sq, splits_before=0, max_splits=6, **kw)
+            used = ops.accel_window(packed, n_src, *own, x, mode, self.G, self.softening_sq, splits_before=0, max_splits=12, **kw)
             for w in others:
                 used = ops.accel_window(packed, n_src, *w, x, mode, self.G, self.softening_sq, splits_before=used, **kw)
             return ops.accel_finish(used, x, mode, self.G, uniform=uni)
         main, side = torch.cuda.current_stream(self.device), self._side_stream()
         packed = self._packed_all
         self._last_packed, self._last_nsrc = packed, n_src
-        ops.accel_workspace(x)                   # allocate the shared scratch on the compute stream before any launch
         ready = torch.cuda.Event()
         ready.record(main)                       # the KDK kernel has written this rank's slot
-        used = ops.accel_window(packed, n_src, *own, x, mode, self.G, self.softening_sq, splits_before=0, max_splits=6, **kw)
         done = torch.cuda.Event()
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side):            # side stream: only the collective
             side.wait_event(ready)
             self._all_gather_packed(local_packed)
-            for w in others:
-                used = ops.accel_window(packed, n_src, *w, x, mode, self.G, self.softening_sq, splits_before=used, **kw)
             done.record(side)
+        used = ops.accel_window(packed, n_src, *own, x, mode, self.G, self.softening_sq, splits_before=0, max_splits=12, **kw)
         main.wait_event(done)
+        for w in others:
+            used = ops.accel_window(packed, n_src, *w, x, mode, self.G, self.softening_sq, splits_before=used, **kw)
         return ops.accel_finish(used, x, mode, self.G, uniform=uni)
 
     def _pe_fusable_dtype(self, dtype) -> bool:
