@@ -99,6 +99,9 @@ int nb_pack_sources(const void* pos, const void* mass, int64_t n, int dim, int d
 /* ---- force evaluation: GalaxySimulation._compute_accelerations, simulation.py:74-118 ------- */
 /* Bytes of scratch nb_accel needs for n_targets targets (partial sums of the j-split). */
 int64_t nb_accel_workspace_bytes(int64_t n_targets, int dim);
+/* Split slots that workspace holds (<= 32 and <= 256 MiB of fp64 partial sums): the budget the windows of one windowed
+ * evaluation (nb_accel_window) share. */
+int nb_accel_max_splits(int64_t n_targets, int dim);
 
 /* INT8_SIM / INT4_SIM / CUSTOM pass 1 (quantization.py:112-113): max over ALL pairs of the n_src packed
  * sources of d² (the reference's exact rounding sequence, state dtype) -> scalars[NB_SLOT_MAX_D2] (atomic max;

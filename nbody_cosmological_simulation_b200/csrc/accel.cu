@@ -1027,6 +1027,10 @@ int launch_accel(const AccelArgs& a0, int64_t workspace_bytes, cudaStream_t st, 
 using namespace nb;
 
 #ifndef NB_TUNE_HARNESS
+extern "C" int nb_accel_max_splits(int64_t n_targets, int dim) {
+    return (n_targets <= 0 || (dim != 2 && dim != 3)) ? 0 : max_splits_for(n_targets, dim);
+}
+
 extern "C" int64_t nb_accel_workspace_bytes(int64_t n_targets, int dim) {
     if (n_targets <= 0 || (dim != 2 && dim != 3)) return 0;
     // room for the largest j-split the planner may choose for this many targets (+ one potential per target and split
@@ -1255,9 +1259,10 @@ static int small_ticks(void* x, void* v, void* acc, const void* mass, int mass_d
     if (dim == 2) rc = uni ? launch_small_ticks<2, true>(p, st) : launch_small_ticks<2, false>(p, st);
     else rc = uni ? launch_small_ticks<3, true>(p, st) : launch_small_ticks<3, false>(p, st);
     if (rc != NB_OK) return rc;
-    // the sums of the last force pass: one "split"
+    // the sums of the last force pass: one "split"; the packed records of the final positions exist only in shared memory
     ps->partial = p.sums[ticks % 3];
     ps->splits = 1;
+    ps->packed_stale = true;
     return NB_OK;
 }
 

@@ -18,6 +18,8 @@ struct PartialSums {
     double phi_scale;        // common mass (uniform-mass pass summed 1/r), else 1
     bool phi_uniform;
     int64_t n_tgt;
+    bool packed_stale;       // the pass that produced these sums did not leave the packed records of its positions in global
+                             // memory (one-barrier small-system kernel keeps them in shared memory): re-pack before reuse
 };
 
 // a contiguous window of the packed source set: chunks [first_chunk, first_chunk + n_chunks)

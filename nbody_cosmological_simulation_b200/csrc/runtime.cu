@@ -47,7 +47,7 @@ int enqueue_tick(const TickArgs& a, bool first, bool deferred, PartialSums* ps, 
     if (deferred) {
         // the plan (split count, scale) is a pure function of the arguments: every tick produces the same descriptor,
         // which is what lets a captured tick body be replayed
-        *ps = now;
+        *ps = now;                                          // (packed_stale = false: the kick kernel above re-emitted the records)
         return NB_OK;
     }
     return accel_reduce(now, a.acc, a.scalars, st);
@@ -109,6 +109,11 @@ extern "C" int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_
         if ((rc = enqueue_tick(a, /*first=*/false, deferred, &ps, st, remaining == 1 ? pe_out : nullptr))) return rc;
     // closing half kick (with the force snap of INT8/INT4) so that the state is observable; in the deferred case the
     // same kernel reduces the last force pass's partial sums and writes `acc`
+    if (deferred && ps.packed_stale) {
+        // the one-barrier kernel kept the packed records in shared memory: leave the records of the final positions behind,
+        // as every other path does (the caller's potential-energy / force evaluations reuse them)
+        if ((rc = nb_pack_sources(x, mass, n, dim, dtype, mass_dtype, packed, 0, st))) return rc;
+    }
     if (deferred)
         return kdk_from_partials(nullptr, v, acc, nullptr, v, n, dim, dtype, dt, NB_KDK_KICK, scalars, mass, mass_dtype, nullptr, 0, ps, st);
     return nb_kdk(nullptr, v, acc, nullptr, v, n, dim, dtype, dt, NB_KDK_KICK, snap_levels, scalars, mass, mass_dtype, nullptr, 0, st);

@@ -100,6 +100,9 @@ class CudaOps:
                                       ws.numel(), L.stream_ptr(x_tgt.device)), "nb_accel")
         return acc
 
+    def accel_max_splits(self, x_tgt) -> int:
+        return int(self.lib.nb_accel_max_splits(x_tgt.shape[0], x_tgt.shape[1]))
+
     def accel_workspace(self, x_tgt):
         n, dim = x_tgt.shape
         return self._scratch("accel", self.lib.nb_accel_workspace_bytes(n, dim), x_tgt.device)

@@ -214,12 +214,21 @@ class ShardedGalaxySimulation:
         # the other slots as contiguous windows: the ones after this rank's, then the ones before it
         others = [w for w in (((self.rank + 1) * slot, (self.world - 1 - self.rank) * slot), (0, self.rank * slot)) if w[1] > 0]
         kw = dict(uniform=uni)
+        # split budget of the shared partial-sum workspace: a quarter (at most 8) for the own slot, the rest shared by the
+        # other windows; too few slots for one per window (huge shards) -> gather first, one launch
+        budget = ops.accel_max_splits(x)
+        if budget < 1 + len(others):
+            packed = self._all_gather_packed(local_packed)
+            self._last_packed, self._last_nsrc = packed, n_src
+            return ops.accel(packed, n_src, x, mode, self.G, self.softening_sq, None, 0, self.scalars, uniform=uni)
+        own_cap = max(1, min(8, budget // 4))
+        other_cap = max(1, (budget - own_cap) // max(1, len(others)))
         if not x.is_cuda:                        # CPU test backends: same windows, no streams
             packed = self._all_gather_packed(local_packed)
             self._last_packed, self._last_nsrc = packed, n_src
-            used = ops.accel_window(packed, n_src, *own, x, mode, self.G, self.softening_sq, splits_before=0, max_splits=12, **kw)
+            used = ops.accel_window(packed, n_src, *own, x, mode, self.G, self.softening_sq, splits_before=0, max_splits=own_cap, **kw)
             for w in others:
-                used = ops.accel_window(packed, n_src, *w, x, mode, self.G, self.softening_sq, splits_before=used, **kw)
+                used = ops.accel_window(packed, n_src, *w, x, mode, self.G, self.softening_sq, splits_before=used, max_splits=other_cap, **kw)
             return ops.accel_finish(used, x, mode, self.G, uniform=uni)
         main, side = torch.cuda.current_stream(self.device), self._side_stream()
         packed = self._packed_all
@@ -231,10 +240,10 @@ class ShardedGalaxySimulation:
             side.wait_event(ready)
             self._all_gather_packed(local_packed)
             done.record(side)
-        used = ops.accel_window(packed, n_src, *own, x, mode, self.G, self.softening_sq, splits_before=0, max_splits=12, **kw)
+        used = ops.accel_window(packed, n_src, *own, x, mode, self.G, self.softening_sq, splits_before=0, max_splits=own_cap, **kw)
         main.wait_event(done)
         for w in others:
-            used = ops.accel_window(packed, n_src, *w, x, mode, self.G, self.softening_sq, splits_before=used, **kw)
+            used = ops.accel_window(packed, n_src, *w, x, mode, self.G, self.softening_sq, splits_before=used, max_splits=other_cap, **kw)
         return ops.accel_finish(used, x, mode, self.G, uniform=uni)
 
     def _pe_fusable_dtype(self, dtype) -> bool:

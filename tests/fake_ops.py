@@ -153,6 +153,9 @@ class FakeOps:
             scalars[L.SLOT_ACC_MAX] = max(int(scalars[L.SLOT_ACC_MAX]), key(acc.max().item()))
         return acc
 
+    def accel_max_splits(self, x_tgt):
+        return 32
+
     def accel_window(self, packed, n_src, first_chunk, n_chunks, x_tgt, mode, G, eps_sq, uniform=(False, 0.0),
                      splits_before=0, max_splits=0):
         """Partial accelerations of one contiguous source window, kept per slot."""
