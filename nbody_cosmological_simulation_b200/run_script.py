@@ -25,7 +25,10 @@ def _join_process_group():
         return
     import torch
     import torch.distributed as dist
-    if not torch.cuda.is_available() or dist.is_initialized():
+    if not torch.cuda.is_available():
+        return
+    os.environ["NB_B200_DISTRIBUTED"] = "1"          # GalaxySimulation's replicated multi-GPU mode is opt-in
+    if dist.is_initialized():
         return
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)

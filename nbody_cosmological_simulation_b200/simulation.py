@@ -62,8 +62,10 @@ class _ReplicatedShards:
     i-range against all sources and the ranks all-gather the accelerations (N·D·w bytes per tick).  The O(N) integrator
     runs redundantly and deterministically on every rank, so the replicas stay bit-identical.  The initial state is
     broadcast from rank 0 (the reference's scripts do not seed their RNG: every rank would draw a different galaxy).
-    Chosen automatically when torch.distributed is initialised with more than one rank; NB_B200_DISTRIBUTED=0 turns it
-    off.  `sharded.ShardedGalaxySimulation` is the engine that also shards the STATE (and hides the gather)."""
+    OPT-IN: active only when NB_B200_DISTRIBUTED=1 and torch.distributed is initialised with more than one rank (every
+    construction and force evaluation is then a collective: ALL ranks must make the same calls; `run_script` sets the
+    switch when it joins the process group under torchrun).  `sharded.ShardedGalaxySimulation` is the engine that also
+    shards the STATE (and hides the gather)."""
 
     def __init__(self, n: int, state_dtype, device):
         import torch.distributed as dist
@@ -87,7 +89,7 @@ class _ReplicatedShards:
             import torch.distributed as dist
         except ImportError:
             return False
-        return (os.environ.get("NB_B200_DISTRIBUTED", "1") != "0" and dist.is_available() and dist.is_initialized()
+        return (os.environ.get("NB_B200_DISTRIBUTED", "0") == "1" and dist.is_available() and dist.is_initialized()
                 and dist.get_world_size() > 1 and torch.device(device).type == "cuda")
 
     def broadcast(self, *tensors):
@@ -422,9 +424,9 @@ class GalaxySimulation:
 
     # below this many particles a tick is launch-latency bound: replay it from a CUDA graph ...
     GRAPH_MAX_STARS = 65536
-    # ... and below this many, run whole spans of ticks as ONE persistent cooperative kernel (fp32 state, FLOAT32 mode):
-    # measured 9.1 / 12.3 / 14.8 us per tick at N = 500 / 1000 / 3000 against 12.4 / 14.4 / 16.4 from the graph, but 58 vs 47
-    # at N = 10 000 (two resident CTAs per SM instead of three) — profiles/r02/README.md
+    # ... and below this many, run whole spans of ticks as ONE persistent cooperative kernel (fp32 state, FLOAT32 mode): the
+    # one-barrier kernel measured 7.3 / 7.5 / 7.6 / 12.3 us per tick at N = 500 / 1000 / 3000 / 4096 against 12.4 / 14.4 /
+    # 16.4 / ~20 from the graph replay (profiles/r02/small_n_one_barrier_vs_two.log)
     PERSISTENT_MAX_STARS = 4096
 
     def _run_fused(self, ticks: int, spec=None):

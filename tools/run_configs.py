@@ -51,8 +51,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.stars or (4_194_304 if args.config == "c4" else 16_777_216)
-    torch.manual_seed(1234)                                  # same stream on every rank -> identical galaxies
-    pos, vel, mass = nb.create_disk_galaxy(n, galaxy_radius=10.0, device=dev)
+    # counter-based initial conditions: every rank generates ONLY its own slice (no rank ever holds the whole galaxy)
+    plan = ShardedGalaxySimulation.plan_for(n, torch.float32)
+    sl = plan.slice(rank)
+    pos, vel, mass = nb.create_disk_galaxy_sharded(n, galaxy_radius=10.0, device=dev, seed=1234, start=sl.start,
+                                                   count=sl.stop - sl.start, collective=world > 1)
     if args.config == "c4":
         ticks = args.ticks or 5
         pos, vel, mass = pos.double(), vel.double(), mass.double()
@@ -60,25 +63,29 @@ def main():
         scale = 1.0 if args.no_rescale else 5000.0 / n
         vel = vel * scale ** 0.5
         sim, t_init = timed(lambda: ShardedGalaxySimulation(pos, vel, mass, precision_mode=nb.PrecisionMode.FLOAT64,
-                                                            G=0.001 * scale), dev, world)
-        e, t_e = timed(sim.get_total_energy, dev, world)
-        energies, tick_ms = [e], []
+                                                            G=0.001 * scale, num_stars=n), dev, world)
+        e, t_e = timed(sim.get_total_energy, dev, world)       # stand-alone potential kernel (no force pass has carried it yet)
+        energies, tick_ms, energy_ms = [e], [], []
         for _ in range(ticks):
-            _, ms = timed(lambda: sim.run(1), dev, world)
+            _, ms = timed(lambda: sim.run(1), dev, world)       # energy was read -> this tick's force pass carries the potential
             tick_ms.append(ms)
-            energies.append(sim.get_total_energy())
+            en, ems = timed(sim.get_total_energy, dev, world)
+            energies.append(en)
+            energy_ms.append(ems)
         if rank == 0:
             best = min(tick_ms)
             print(json.dumps({"config": "c4: disk galaxy float64 energy tracking", "n_particles": n, "n_gpus": world, "ticks": ticks,
                               "ms_per_tick": tick_ms, "interactions_per_s": n * float(n) / (best * 1e-3),
                               "tflops_at_20_flop": 20 * n * float(n) / (best * 1e-3) / 1e12, "init_force_ms": t_init,
-                              "total_energy_ms": t_e, "energies": energies, "G": 0.001 * scale,
+                              "total_energy_ms_standalone": t_e, "total_energy_ms_after_tick": energy_ms, "energies": energies,
+                              "G": 0.001 * scale, "initial_conditions": "create_disk_galaxy_sharded (each rank its own slice)",
                               "max_rel_energy_drift": max(abs(x - energies[0]) for x in energies) / abs(energies[0])}), flush=True)
     else:
         ticks = args.ticks or 1
         pos, vel, mass = pos.float(), vel.float(), mass.float()
         for mode in args.modes.split(","):
-            sim, t_init = timed(lambda: ShardedGalaxySimulation(pos, vel, mass, precision_mode=nb.get_mode_from_string(mode)), dev, world)
+            sim, t_init = timed(lambda: ShardedGalaxySimulation(pos, vel, mass, precision_mode=nb.get_mode_from_string(mode),
+                                                                num_stars=n), dev, world)
             _, ms = timed(lambda: sim.run(ticks), dev, world)
             distinct = torch.unique(sim.accelerations).numel()
             d = torch.tensor([distinct], device=dev)

@@ -23,6 +23,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    os.environ["NB_B200_DISTRIBUTED"] = "1"              # opt in (run_script does this for unchanged scripts)
     ok = True
     for n, mode, dtype in ((6000, "float32", torch.float32), (6000, "int4_sim", torch.float32), (3000, "float64", torch.float32),
                            (4100, "float64", torch.float64), (300, "float32", torch.float32), (5000, "float16", torch.float32)):
