@@ -190,6 +190,8 @@ def sha256_of(*tensors):
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("NB_BENCH_WATCHDOG_S", "900")), exit=False)   # a stuck collective leaves a stack, not silence
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -16,6 +16,8 @@ from oracle import reference_port as ora  # noqa: E402  (synthetic inputs only)
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(200, exit=False)
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
