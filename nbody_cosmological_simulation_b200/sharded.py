@@ -30,7 +30,13 @@ from . import _lib as L
 from .quantization import PrecisionMode, levels_for_mode
 
 _INT_FORCE_SNAP = {PrecisionMode.INT8_SIM: 256, PrecisionMode.INT4_SIM: 16}
-_OVERLAP = os.environ.get("NB_B200_OVERLAP", "1") != "0"       # all-gather hidden behind the own-slot force window
+# how the per-tick all-gather of the packed sources meets the pair kernel (float modes, >1 rank):
+#   0  gather, then ONE launch over all slots
+#   1  own-slot window at once, gather on a side stream, then the other slots' windows on the compute stream
+#   2  as 1, but the other windows run on side streams too, CONCURRENTLY with the own window: no launch drains alone, the
+#      windows' tails fill each other (one launch's tail costs about half a CTA lifetime; that is what made 1 lose 3 % at N=2)
+_OVERLAP_MODE = int(os.environ.get("NB_B200_OVERLAP", "2"))
+_OVERLAP = _OVERLAP_MODE != 0
 
 
 class ShardPlan:
@@ -155,10 +161,11 @@ class ShardedGalaxySimulation:
             setattr(self, key, buf)
         return buf
 
-    def _side_stream(self):
-        if getattr(self, "_comm_stream", None) is None:
-            self._comm_stream = torch.cuda.Stream(device=self.device)
-        return self._comm_stream
+    def _side_stream(self, which: int = 0):
+        streams = self.__dict__.setdefault("_side_streams", {})
+        if which not in streams:
+            streams[which] = torch.cuda.Stream(device=self.device)
+        return streams[which]
 
     def pair_launches_next_tick(self) -> int:
         """How many pair-kernel launches the next tick's force evaluation makes (instrumentation: _lib.ForceTimer.arm)."""
@@ -206,8 +213,9 @@ class ShardedGalaxySimulation:
         """Float modes on several ranks.  Compute stream: the pair kernel over this rank's OWN slot (1/P of the work)
         starts at once.  Side stream: the in-place all-gather of the other slots.  Compute stream again, once the gather
         is done: the pair kernel over the slots after and before this rank's (two contiguous windows, the same kernel image
-        as a single-GPU run).  (Launching those on the side stream too, so that they overlap the tail of the first window,
-        hung on 2 GPUs in session E and was withdrawn.)  One reduction over the split slots of all windows follows."""
+        as a single-GPU run) — on side streams (NB_B200_OVERLAP=2, default), so that all windows are in flight together
+        and no launch drains alone, or on the compute stream (=1).  One reduction over the split slots of all windows
+        follows."""
         ops, mode, uni = self.ops, self.precision_mode.value, self._uniform_mass()
         slot = plan.slot_chunks
         own = (self.rank * slot, slot)
@@ -241,9 +249,22 @@ class ShardedGalaxySimulation:
             self._all_gather_packed(local_packed)
             done.record(side)
         used = ops.accel_window(packed, n_src, *own, x, mode, self.G, self.softening_sq, splits_before=0, max_splits=own_cap, **kw)
-        main.wait_event(done)
-        for w in others:
-            used = ops.accel_window(packed, n_src, *w, x, mode, self.G, self.softening_sq, splits_before=used, max_splits=other_cap, **kw)
+        if _OVERLAP_MODE == 1:
+            main.wait_event(done)
+            for w in others:
+                used = ops.accel_window(packed, n_src, *w, x, mode, self.G, self.softening_sq, splits_before=used, max_splits=other_cap, **kw)
+            return ops.accel_finish(used, x, mode, self.G, uniform=uni)
+        # mode 2: every other window on its own side stream behind the gather (they write disjoint split slots of the
+        # workspace, so nothing orders them among themselves); the compute stream joins them before the reduction
+        for k, w in enumerate(others):
+            st = self._side_stream(k)
+            with torch.cuda.stream(st):
+                if k:
+                    st.wait_event(done)
+                used = ops.accel_window(packed, n_src, *w, x, mode, self.G, self.softening_sq, splits_before=used, max_splits=other_cap, **kw)
+                fin = torch.cuda.Event()
+                fin.record(st)
+            main.wait_event(fin)
         return ops.accel_finish(used, x, mode, self.G, uniform=uni)
 
     def _pe_fusable_dtype(self, dtype) -> bool:
