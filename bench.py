@@ -291,9 +291,10 @@ def main():
     value = interactions_per_step / (ms_per_step * 1e-3)
     f_ms = max_over_ranks(sum(force_ms) / len(force_ms))
     # kernels of this library per step and rank: 1 GPU: kick-drift(+packed emit), pair kernel, closing kick (which also
-    # reduces the j-split partial sums) = 3; sharded: kick-drift, pair kernel on the own slot, pair kernel on the gathered
-    # slots, partial-sum reduction, closing kick = 5 (+1 NCCL all-gather); profiles/r02/bench_n1_launch_list.csv
-    launches = K * (3 if world == 1 else 5)
+    # reduces the j-split partial sums) = 3; sharded: kick-drift(+packed emit into the rank's slot), pair kernel over the
+    # gathered slots, partial-sum reduction, closing kick = 4 (+1 NCCL all-gather, not counted); NB_B200_OVERLAP=1/2 split the
+    # pair kernel into one launch per source window; profiles/r02/bench_n1_launch_list.csv
+    launches = K * (3 if world == 1 else 3 + sim.pair_launches_next_tick())
 
     # -------- end to end through the public API with host buffers (pinned), same metric --------
     sl = sim.plan.slice(rank) if world > 1 else slice(0, N_PARTICLES)
@@ -451,8 +452,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_dict(world),
-                "parallelism": (f"i-range shards x{world}; packed sources all-gathered in place per tick on a side stream, hidden behind "
-                                f"the pair kernel over the rank's own slot") if world > 1 else "single GPU",
+                "parallelism": (f"i-range shards x{world}; packed sources (16 B per star) all-gathered in place once per tick over "
+                                f"NCCL, then one pair-kernel launch per rank (NB_B200_OVERLAP={os.environ.get('NB_B200_OVERLAP', '0')})")
+                if world > 1 else "single GPU",
                 "l2": "flushed between steps (192 MiB write inside the timed region); the 16 MiB packed source set is "
                       "re-read from L2 by design",
                 "tflops_at_20_flop": value * FLOP_PER_INTERACTION / 1e12,

@@ -31,11 +31,13 @@ from .quantization import PrecisionMode, levels_for_mode
 
 _INT_FORCE_SNAP = {PrecisionMode.INT8_SIM: 256, PrecisionMode.INT4_SIM: 16}
 # how the per-tick all-gather of the packed sources meets the pair kernel (float modes, >1 rank):
-#   0  gather, then ONE launch over all slots
+#   0  gather (8-16 MB in place over NVLink: ~0.1-0.3 ms), then ONE launch over all slots          <- default
 #   1  own-slot window at once, gather on a side stream, then the other slots' windows on the compute stream
-#   2  as 1, but the other windows run on side streams too, CONCURRENTLY with the own window: no launch drains alone, the
-#      windows' tails fill each other (one launch's tail costs about half a CTA lifetime; that is what made 1 lose 3 % at N=2)
-_OVERLAP_MODE = int(os.environ.get("NB_B200_OVERLAP", "2"))
+#   2  as 1, but the other windows run on side streams too, concurrently with the own window
+# Measured on 2 B200s at N = 2^20, one process group, alternating (profiles/r02/overlap_ab_n2.log): 0: 194.4 / 194.7 ms per
+# tick, 1: 195.6 / 200.3, 2: 202.4 / 198.1 — hiding a 0.3 ms collective costs more (every extra launch drains alone, two
+# co-resident grids disturb each other's waves) than it saves, so the hidden variants stay switchable but are not the default.
+_OVERLAP_MODE = int(os.environ.get("NB_B200_OVERLAP", "0"))
 _OVERLAP = _OVERLAP_MODE != 0
 
 

@@ -53,7 +53,7 @@ def test_fake_pack_roundtrip_matches_layout_spec():
             assert (px[n:] > 1e17).all() and (pm[n:] == 0).all()          # pads: far away, zero mass
 
 
-def _worker(rank, world, port, mode, n, dim, ticks, out):
+def _worker(rank, world, port, mode, n, dim, ticks, out, overlap=0):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -62,8 +62,10 @@ def _worker(rank, world, port, mode, n, dim, ticks, out):
     try:
         from fake_ops import FakeOps
         import nbody_cosmological_simulation_b200 as nb
+        from nbody_cosmological_simulation_b200 import sharded
         from nbody_cosmological_simulation_b200.sharded import ShardedGalaxySimulation
         from oracle import reference_port as ora
+        sharded._OVERLAP_MODE, sharded._OVERLAP = overlap, overlap != 0      # 0: gather + one launch; 1: source windows
         if dim == 2:
             torch.manual_seed(3)
             pos, vel, mass = nb.create_disk_galaxy(n, device=torch.device("cpu"))
@@ -83,14 +85,14 @@ def _worker(rank, world, port, mode, n, dim, ticks, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,mode,n,dim", [(2, "float32", 700, 2), (2, "int4_sim", 700, 2), (3, "float64", 900, 3),
-                                              (2, "float16", 600, 3)])
-def test_sharded_run_matches_single_process_oracle(tmp_path, world, mode, n, dim):
+@pytest.mark.parametrize("world,mode,n,dim,overlap", [(2, "float32", 700, 2, 0), (2, "float32", 700, 2, 1), (2, "int4_sim", 700, 2, 0),
+                                                      (3, "float64", 900, 3, 1), (3, "float64", 900, 3, 0), (2, "float16", 600, 3, 0)])
+def test_sharded_run_matches_single_process_oracle(tmp_path, world, mode, n, dim, overlap):
     from oracle import reference_port as ora
     import nbody_cosmological_simulation_b200 as nb
     out = str(tmp_path / "r0.pt")
     ticks = 3
-    mp.spawn(_worker, args=(world, _free_port(), mode, n, dim, ticks, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), mode, n, dim, ticks, out, overlap), nprocs=world, join=True)
     got = torch.load(out)
     if dim == 2:
         torch.manual_seed(3)
