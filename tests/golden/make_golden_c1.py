@@ -30,6 +30,9 @@ def main():
     ap.add_argument("--threads", type=int, default=4)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--add-perturbed-int4", action="store_true",
+                    help="append `int4_sim/total_perturbed` to an EXISTING fixture: the reference's own int4 run from the same "
+                         "state with positions[0, 0] moved by one ulp — how far the reference is from itself after 2000 ticks")
     args = ap.parse_args()
     sys.path.insert(0, args.ref)
     import galaxy as rgalaxy
@@ -39,6 +42,8 @@ def main():
 
     torch.set_num_threads(args.threads)
     dev = torch.device("cpu")
+    if args.add_perturbed_int4:
+        return add_perturbed_int4(args, rsim, rquant)
     torch.manual_seed(args.seed)
     pos, vel, mass = rgalaxy.create_disk_galaxy(num_stars=args.stars, galaxy_radius=10.0, device=dev)   # main.py:124
     pos, vel, mass = pos.float(), vel.float(), mass.float()                                             # main.py:131-133
@@ -76,6 +81,25 @@ def main():
     path = args.out or os.path.join(HERE, f"c1_disk{args.stars}.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path} ({os.path.getsize(path)} bytes)")
+
+
+def add_perturbed_int4(args, rsim, rquant):
+    path = args.out or os.path.join(HERE, f"c1_disk{args.stars}.npz")
+    g = dict(np.load(path))
+    pos, vel, mass = (torch.from_numpy(g[k]) for k in ("pos", "vel", "mass"))
+    pos = pos.clone()
+    pos[0, 0] = torch.nextafter(pos[0, 0], torch.tensor(100.0))                  # one ulp, one coordinate, one star
+    sim = rsim.GalaxySimulation(pos, vel, mass, precision_mode=rquant.PrecisionMode.INT4_SIM, G=float(g["G"]), dt=float(g["dt"]),
+                                device=torch.device("cpu"))
+    total, t0 = [float(g["int4_sim/total"][0])], time.time()
+    for t in range(1, int(g["ticks"]) + 1):
+        sim.step()
+        if t % 100 == 0:
+            total.append(sim.get_total_energy())
+            print(f"perturbed int4 tick {t} E={total[-1]:.6f} (unperturbed {g['int4_sim/total'][t // 100]:.6f}) {time.time() - t0:.0f}s", flush=True)
+    g["int4_sim/total_perturbed"] = np.array(total, dtype=np.float64)
+    np.savez_compressed(path, **g)
+    print(f"appended int4_sim/total_perturbed to {path}")
 
 
 if __name__ == "__main__":
