@@ -30,9 +30,13 @@ def main():
     ap.add_argument("--threads", type=int, default=4)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--out", default=None)
-    ap.add_argument("--add-perturbed-int4", action="store_true",
-                    help="append `int4_sim/total_perturbed` to an EXISTING fixture: the reference's own int4 run from the same "
-                         "state with positions[0, 0] moved by one ulp — how far the reference is from itself after 2000 ticks")
+    ap.add_argument("--out-series", default=None, help="with --add-perturbed-int4: write the series to this .npy instead of the fixture")
+    ap.add_argument("--add-perturbed-int4", default=None, metavar="one|all:SEED",
+                    help="append to an EXISTING fixture the reference's own int4 energy series from the same state with "
+                         "positions[0, 0] moved by one ulp (`one` -> key int4_sim/total_perturbed) or with EVERY coordinate moved "
+                         "by -1/0/+1 ulp at random (`all:SEED` -> key int4_sim/total_perturbed_all_SEED; this is the size of the "
+                         "difference between two correct fp32 evaluations of the same forces) — how far the reference is from "
+                         "itself after 2000 ticks")
     args = ap.parse_args()
     sys.path.insert(0, args.ref)
     import galaxy as rgalaxy
@@ -88,7 +92,15 @@ def add_perturbed_int4(args, rsim, rquant):
     g = dict(np.load(path))
     pos, vel, mass = (torch.from_numpy(g[k]) for k in ("pos", "vel", "mass"))
     pos = pos.clone()
-    pos[0, 0] = torch.nextafter(pos[0, 0], torch.tensor(100.0))                  # one ulp, one coordinate, one star
+    if args.add_perturbed_int4 == "one":
+        key = "int4_sim/total_perturbed"
+        pos[0, 0] = torch.nextafter(pos[0, 0], torch.tensor(100.0))              # one ulp, one coordinate, one star
+    else:
+        seed = int(args.add_perturbed_int4.split(":")[1])
+        key = f"int4_sim/total_perturbed_all_{seed}"
+        step = torch.randint(-1, 2, pos.shape, generator=torch.Generator().manual_seed(seed))
+        up, down = torch.nextafter(pos, torch.full_like(pos, 1e9)), torch.nextafter(pos, torch.full_like(pos, -1e9))
+        pos = torch.where(step > 0, up, torch.where(step < 0, down, pos))
     sim = rsim.GalaxySimulation(pos, vel, mass, precision_mode=rquant.PrecisionMode.INT4_SIM, G=float(g["G"]), dt=float(g["dt"]),
                                 device=torch.device("cpu"))
     total, t0 = [float(g["int4_sim/total"][0])], time.time()
@@ -97,9 +109,13 @@ def add_perturbed_int4(args, rsim, rquant):
         if t % 100 == 0:
             total.append(sim.get_total_energy())
             print(f"perturbed int4 tick {t} E={total[-1]:.6f} (unperturbed {g['int4_sim/total'][t // 100]:.6f}) {time.time() - t0:.0f}s", flush=True)
-    g["int4_sim/total_perturbed"] = np.array(total, dtype=np.float64)
+    if args.out_series:
+        np.save(args.out_series, np.array(total, dtype=np.float64))             # parallel runs: merge afterwards
+        return
+    g = dict(np.load(path))
+    g[key] = np.array(total, dtype=np.float64)
     np.savez_compressed(path, **g)
-    print(f"appended int4_sim/total_perturbed to {path}")
+    print(f"appended {key} to {path}")
 
 
 if __name__ == "__main__":
