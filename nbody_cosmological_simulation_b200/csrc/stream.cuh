@@ -64,11 +64,14 @@ inline SplitPlan plan_splits(int64_t n_tgt, int64_t n_chunks, int targets_per_bl
     return best;
 }
 
-// upper bound on the split count used for sizing workspaces (<= 256 MiB of partial sums, <= 32 splits)
+// upper bound on the split count used for sizing workspaces (<= 256 MiB of partial sums, <= 32 splits;
+// NB_B200_SPLIT_WORKSPACE_MB / NB_B200_SPLIT_CAP: developer overrides for A/B timing, never set in production)
 inline int max_splits_for(int64_t n_tgt, int dim) {
+    static const int64_t mb = [] { const char* e = getenv("NB_B200_SPLIT_WORKSPACE_MB"); return e && atoi(e) > 0 ? (int64_t)atoi(e) : (int64_t)256; }();
+    static const int64_t hard = [] { const char* e = getenv("NB_B200_SPLIT_CAP"); return e && atoi(e) > 0 ? (int64_t)atoi(e) : (int64_t)32; }();
     const int64_t per_split = n_tgt * dim * (int64_t)sizeof(double);
-    int64_t s = ((int64_t)256 << 20) / (per_split > 0 ? per_split : 1);
-    if (s > 32) s = 32;
+    int64_t s = (mb << 20) / (per_split > 0 ? per_split : 1);
+    if (s > hard) s = hard;
     if (s < 1) s = 1;
     return (int)s;
 }
