@@ -314,9 +314,24 @@ def test_c1_int4_energy_series(c1):
     d_early = (early_e - e0) / abs(e0)
     d_early_ref = (c1["int4_sim/early_total"] - e0) / abs(e0)
     assert np.all(np.abs(d_early - d_early_ref) <= np.maximum(1e-6, 0.05 * np.abs(d_early_ref))), (d_early, d_early_ref)
-    # whole run: a 16-level force grid makes the trajectory chaotic (a single flipped level re-snaps every
-    # acceleration), so the long series is compared as a curve: same sign, same magnitude (the reference drifts
-    # +9 % here), never further from the reference than a quarter of the reference's own maximum drift
-    # (N = 5000: reference drift up to 0.21, the CUDA path stays within 0.06 of it at every sample)
-    assert np.all(np.abs(drift - drift_ref) <= 0.35 * np.abs(drift_ref).max()), (drift, drift_ref)
-    assert abs(drift[-1] - drift_ref[-1]) <= 0.5 * abs(drift_ref[-1])
+    # whole run: a 16-level force grid makes the trajectory chaotic (a single flipped level re-snaps every acceleration), so
+    # the long series is compared as a curve.
+    family = [c1[k] for k in sorted(c1.files) if k.startswith("int4_sim/total_perturbed")]
+    if family:
+        # N = 5000 ("fall back to multi-seed ... only if a level flip makes int-mode trajectories diverge"): the
+        # fixture carries the REFERENCE's own series from the same state with one coordinate moved by one ulp and (twice) with
+        # every coordinate moved by -1/0/+1 ulp — the size of the difference between two correct fp32 evaluations.  Those four
+        # reference curves agree to 5 % for 100 ticks and then fan out to 0.12 ... 0.33 (profiles/r02/int4_chaos_n5000.log shows
+        # the same fan for the CUDA path).  The CUDA curve must stay inside the reference family's envelope, widened by a
+        # quarter of the family's largest width.
+        fam = np.array([(f - e0) / abs(e0) for f in [ref] + family])
+        lo, hi = fam.min(0), fam.max(0)
+        margin = 0.25 * (hi - lo).max()
+        assert np.all(drift >= lo - margin) and np.all(drift <= hi + margin), (drift, lo, hi, margin)
+        assert drift[-1] > 0.5 * lo[-1]                                     # the heating is there, with the reference's sign
+    else:
+        # N = 2000: same sign, same magnitude (the reference drifts +9 % here), never further from the reference than 0.35 of
+        # the reference's own maximum drift (profiles/r02/int4_chaos_n2000.log: eight CUDA runs one ulp apart stay within 0.043
+        # of each other and 0.039 of the reference, 0.35 * max = 0.045)
+        assert np.all(np.abs(drift - drift_ref) <= 0.35 * np.abs(drift_ref).max()), (drift, drift_ref)
+        assert abs(drift[-1] - drift_ref[-1]) <= 0.5 * abs(drift_ref[-1])

@@ -46,6 +46,23 @@ def main():
             if rank == 0:
                 h = hashlib.sha256(st["positions"].cpu().numpy().tobytes() + st["velocities"].cpu().numpy().tobytes()).hexdigest()[:16]
                 print(f"world={world} N={n} NB_B200_OVERLAP={mode} rep={rep}: {t.item():.3f} ms/tick  state sha256 {h}", flush=True)
+            if mode == 0 and rep == 0:
+                # the collective alone: in-place all-gather of the packed slots, CUDA events on its stream, max over ranks
+                plan = sim._plan_for(torch.float32)
+                local = sim._local_packed_buffer(torch.float32)
+                for _ in range(3):
+                    sim._all_gather_packed(local)
+                torch.cuda.synchronize(); dist.barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(20):
+                    sim._all_gather_packed(local)
+                g1.record(); torch.cuda.synchronize()
+                tg = torch.tensor([g0.elapsed_time(g1) / 20], device=dev)
+                dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+                if rank == 0:
+                    print(f"world={world} N={n} all-gather of the packed sources ({plan.padded_sources * 16 / 1e6:.1f} MB total): "
+                          f"{tg.item() * 1e3:.1f} us back to back (max over ranks)", flush=True)
             del sim
     dist.barrier()
     dist.destroy_process_group()
