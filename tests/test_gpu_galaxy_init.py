@@ -10,7 +10,6 @@ pin the draws; its FORMULAS and DISTRIBUTIONS are what must match):
     is N(0, sigma²) with sigma = 0.1 (0.05) x mean circular speed;
   * statistics agree with the torch-stream recipe `create_disk_galaxy` at the same N.
 """
-import ctypes
 import math
 
 import numpy as np

@@ -1,7 +1,6 @@
 """The fused kick-drift-kick kernels through the C ABI: vectorised (16-byte aligned) and element-wise paths must be
 bit-identical to torch's separately rounded `v + a*(dt/2)`, `x + v*dt` (simulation.py:132-141), for every phase,
 dtype, dimension and ragged size; the packed records they emit must equal nb_pack_sources of the new positions."""
-import numpy as np
 import pytest
 import torch
 

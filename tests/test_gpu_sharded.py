@@ -1,6 +1,5 @@
 """CUDA path of the sharded engine on one GPU (world_size 1) and, when launched under torchrun with NCCL,
 on several (tools/run_sharded_check.py drives that case)."""
-import numpy as np
 import pytest
 import torch
 
