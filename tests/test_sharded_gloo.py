@@ -116,3 +116,29 @@ def test_sharded_run_matches_single_process_oracle(tmp_path, world, mode, n, dim
         np.testing.assert_allclose(got["vel"].numpy(), ref.vel.numpy(), rtol=0, atol=1e-6)
     assert abs(got["e0"] - e0) <= 5e-6 * abs(e0)
     assert abs(got["e1"] - ref.total()) <= (2e-3 if mode == "int4_sim" else 5e-6) * abs(e0)
+
+
+def _optin_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nbody_cosmological_simulation_b200.simulation import _ReplicatedShards
+        res = []
+        for val in (None, "0", "1"):
+            os.environ.pop("NB_B200_DISTRIBUTED", None)
+            if val is not None:
+                os.environ["NB_B200_DISTRIBUTED"] = val
+            res.append((_ReplicatedShards.wanted("cuda:0"), _ReplicatedShards.wanted("cpu")))
+        if rank == 0:
+            torch.save(res, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicated_mode_is_opt_in(tmp_path):
+    """An initialised process group alone must not turn GalaxySimulation's constructor into a collective (a rank-local twin
+    built by one rank only would deadlock — bench.py's parity leg does exactly that); NB_B200_DISTRIBUTED=1 opts in."""
+    out = str(tmp_path / "optin.pt")
+    mp.spawn(_optin_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert torch.load(out) == [(False, False), (False, False), (True, False)]
