@@ -162,9 +162,10 @@ int nb_accel_potential(const void* packed_src, int64_t n_src, const void* pos_tg
  * nb_accel_window streams the contiguous source chunks [first_chunk, first_chunk + n_chunks) of the packed set with the
  * same kernels as nb_accel and APPENDS its j-split partial sums to `workspace` behind the `splits_before` split slots
  * earlier windows of the same evaluation wrote; *splits_total_out = splits_before + the slots it added (max_splits > 0 caps
- * them).  nb_accel_finish reduces all slots into acc_out exactly as nb_accel does.  A sharded tick runs the window of the
+ * them).  nb_accel_finish reduces all slots into acc_out exactly as nb_accel does.  A sharded tick can run the window of the
  * rank's OWN packed slot while the all-gather of the other ranks' slots is still in flight, then the windows over the
- * slots after and before its own: the collective hides behind 1/P of the pair work. */
+ * slots after and before its own (NB_B200_OVERLAP=1|2); measured on B200 the plain order — gather, then one nb_accel over
+ * all slots — is faster and is what ShardedGalaxySimulation does by default. */
 int nb_accel_window(const void* packed_src, int64_t n_src, int64_t first_chunk, int64_t n_chunks,
                     const void* pos_tgt, int64_t n_tgt, int dim, int dtype, int mode, double G, double eps_sq,
                     int uniform_mass, double mass_value, void* workspace, int64_t workspace_bytes, int splits_before,
