@@ -55,6 +55,21 @@ inline SplitPlan plan_splits(int64_t n_tgt, int64_t n_chunks, int targets_per_bl
         if (eff > best_eff * 1.0005) { best_eff = eff; best.splits = (int)splits; best.chunks_per_split = (int)cps; }
     }
     if (best_eff < 0) { best.splits = 1; best.chunks_per_split = (int)n_chunks; }
+    // The wave model is blind to the ragged END of a launch (the SMs do not finish together: about 0.2 CTA lifetimes of
+    // idle time, fitted on the fp32 and fast-lookup kernels).  That matters exactly when it picked ONE split for a multi-wave
+    // grid — every CTA then streams the whole source set (84 ms at N = 2^20 in the fast-lookup kernel, whose 2048 x s CTAs fill
+    // 296 slots equally badly for every s): take the largest split count the model rates within 0.1 % of its choice whose CTAs
+    // still stream >= 256 chunks.  Measured: 585.0 -> 571.7 ms (INT8_SIM, D = 3, N = 2^20; profiles/r02/int_splits_ab.log).
+    if (best.splits == 1 && (double)best.blocks_i > slots) {
+        for (int64_t s = max_splits < n_chunks ? max_splits : n_chunks; s > 1; --s) {
+            const int64_t cps = (n_chunks + s - 1) / s;
+            const int64_t splits = (n_chunks + cps - 1) / cps;
+            if (splits != s || cps < 256) continue;
+            const double waves = ceil((double)best.blocks_i * (double)splits / slots);
+            const double eff = ((double)best.blocks_i * (double)n_chunks) / (waves * slots * ((double)cps + 0.2));
+            if (eff >= best_eff * 0.999) { best.splits = (int)splits; best.chunks_per_split = (int)cps; break; }
+        }
+    }
     // developer override for A/B timing of the split count (tools/time_splits.py); never set in production
     static const int forced = [] { const char* e = getenv("NB_B200_SPLITS"); return e ? atoi(e) : 0; }();
     if (forced > 0 && forced <= max_splits && forced <= n_chunks) {
