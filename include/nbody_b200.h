@@ -102,6 +102,11 @@ int64_t nb_accel_workspace_bytes(int64_t n_targets, int dim);
 /* Split slots that workspace holds (<= 32 and <= 256 MiB of fp64 partial sums): the budget the windows of one windowed
  * evaluation (nb_accel_window) share. */
 int nb_accel_max_splits(int64_t n_targets, int dim);
+/* The j-split plan a pair-kernel launch would use (host arithmetic only, no launch): n_targets targets in blocks of
+ * targets_per_block, n_chunks source chunks, ctas_per_sm resident CTAs per SM (148 SMs assumed when no device is present),
+ * at most max_splits splits.  Test / tooling probe of the wave planner. */
+int nb_plan_splits(int64_t n_targets, int64_t n_chunks, int targets_per_block, int ctas_per_sm, int max_splits,
+                   int* splits_out, int* chunks_per_split_out, int* target_blocks_out);
 
 /* INT8_SIM / INT4_SIM / CUSTOM pass 1 (quantization.py:112-113): max over ALL pairs of the n_src packed
  * sources of d² (the reference's exact rounding sequence, state dtype) -> scalars[NB_SLOT_MAX_D2] (atomic max;

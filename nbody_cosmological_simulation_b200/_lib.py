@@ -39,6 +39,7 @@ PROTOTYPES = {
     "nb_pack_sources": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, c_int64, _P]),
     "nb_accel_workspace_bytes": (c_int64, [c_int64, c_int]),
     "nb_accel_max_splits": (c_int, [c_int64, c_int]),
+    "nb_plan_splits": (c_int, [c_int64, c_int64, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "nb_max_dist_workspace_bytes": (c_int64, [c_int64]),
     "nb_max_dist_sq": (c_int, [_P, c_int64, c_int, c_int, c_double, _P, _P, c_int64, _P]),
     "nb_level_table_bytes": (c_int64, [c_int]),

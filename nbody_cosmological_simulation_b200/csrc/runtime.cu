@@ -7,6 +7,7 @@
 // one cudaGraphLaunch.
 #include "common.cuh"
 #include "internal.cuh"
+#include "stream.cuh"
 
 using namespace nb;
 
@@ -117,4 +118,14 @@ extern "C" int nb_run_ticks(const void* x_in, const void* v_in, const void* acc_
     if (deferred)
         return kdk_from_partials(nullptr, v, acc, nullptr, v, n, dim, dtype, dt, NB_KDK_KICK, scalars, mass, mass_dtype, nullptr, 0, ps, st);
     return nb_kdk(nullptr, v, acc, nullptr, v, n, dim, dtype, dt, NB_KDK_KICK, snap_levels, scalars, mass, mass_dtype, nullptr, 0, st);
+}
+
+extern "C" int nb_plan_splits(int64_t n_targets, int64_t n_chunks, int targets_per_block, int ctas_per_sm, int max_splits,
+                              int* splits_out, int* chunks_per_split_out, int* target_blocks_out) {
+    if (n_targets <= 0 || n_chunks <= 0 || targets_per_block <= 0 || max_splits <= 0) return NB_ERR_INVALID_ARGUMENT;
+    const nb::SplitPlan p = nb::plan_splits(n_targets, n_chunks, targets_per_block, ctas_per_sm, max_splits);
+    if (splits_out) *splits_out = p.splits;
+    if (chunks_per_split_out) *chunks_per_split_out = p.chunks_per_split;
+    if (target_blocks_out) *target_blocks_out = p.blocks_i;
+    return NB_OK;
 }
